@@ -1,0 +1,156 @@
+/* qtb.h — C ABI of libqtb.so, the B200-native (sm_100a) engine for QuantiT's block-sparse tensor hot path.
+ *
+ * The reference (AlexandreFoley/QuantiT) has no FFI: its boundary is the public C++ API in namespace quantit.
+ * Every entry point below names the reference interface it replaces (path relative to the reference root, file:line).
+ * A thin C++ adaptor converts `const quantit::btensor&` to the plain arrays taken here, using only
+ * public accessors (btensor.h:215,216,250,276,289,292,795), and rebuilds a btensor from the arrays returned here
+ * through the public raw constructor (btensor.h:168) with every block a zero-copy view of the device arena.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; all integers int64_t unless noted; all data fp64.
+ *  - every function returns a qtb_status; no exception crosses the ABI; qtb_last_error() gives the message
+ *    (thread-local). The adaptor maps statuses back to the exception types the reference throws (see enum).
+ *  - a block tensor = (rank, sections per dim, section sizes, section charges, selection rule, sorted block table,
+ *    ONE device arena). Charges are nc-component integer tuples; `mods[c]` = 0 for a Z component, N for C<N>
+ *    (reference include/Conserved/quantity.h:62-239). Block order is ascending lexicographic on the block index
+ *    (reference include/blockTensor/flat_map.h:31,151).
+ *  - one host thread per context (the reference is single-threaded); work is stream-ordered on the
+ *    context's CUDA stream. There is NO CPU fallback: every compute entry point fails with QTB_ERR_NO_DEVICE
+ *    when no CUDA device is usable.
+ */
+#ifndef QTB_H
+#define QTB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum qtb_status
+{
+	QTB_OK = 0,
+	QTB_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument  (btensor.cpp:390-395,501-517; bad_selection_rule, …) */
+	QTB_ERR_OUT_OF_RANGE = 2,     /* std::out_of_range      (flat_map.h:232, btensor::block_at)                   */
+	QTB_ERR_DOMAIN = 3,           /* std::domain_error      (btensor.cpp:399-404)                                 */
+	QTB_ERR_LOGIC = 4,            /* std::logic_error       (NaN in eig2x2Mat, dmrg.cpp:566-569)                  */
+	QTB_ERR_RUNTIME = 5,          /* std::runtime_error     (dmrg.cpp:261-263)                                    */
+	QTB_ERR_CHECK = 6,            /* c10::Error from TORCH_CHECK (btensor.cpp:802,819,844-846)                    */
+	QTB_ERR_CUDA = 7,             /* a CUDA runtime call failed                                                   */
+	QTB_ERR_NO_DEVICE = 8         /* no usable CUDA device: the engine refuses to run (no CPU fallback)           */
+} qtb_status;
+
+typedef struct qtb_ctx qtb_ctx;       /* device + stream + memory pool + plan cache                    */
+typedef struct qtb_tensor qtb_tensor; /* host block table + (shared, ref-counted) device arena         */
+
+const char *qtb_last_error(void);
+const char *qtb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+/* stream == NULL: the context creates its own non-blocking stream. Otherwise `stream` is a cudaStream_t the caller
+ * owns (e.g. torch's current stream). */
+qtb_status qtb_ctx_create(int device, void *stream, qtb_ctx **out);
+void qtb_ctx_destroy(qtb_ctx *ctx);
+qtb_status qtb_ctx_sync(qtb_ctx *ctx);
+void *qtb_ctx_stream(qtb_ctx *ctx);
+/* counters since context creation: [0] kernel launches of this library, [1] grouped-GEMM launches,
+ * [2] plans built, [3] plan-cache hits, [4] bytes host->device, [5] bytes device->host,
+ * [6] algorithmic GEMM flops issued (sum 2mnk), [7] device bytes currently allocated */
+qtb_status qtb_ctx_counters(qtb_ctx *ctx, int64_t out[8]);
+
+/* ---- tensors: storage (replaces class btensor's block list, btensor.h:105-110,821-837) ---------------------- */
+/* Create from host data. `block_index` is [nblocks*rank] in any order (sorted internally); `host_data` holds the
+ * blocks back to back in the GIVEN order, each C-contiguous with the dims implied by its sections; NULL = zeros.
+ * Mirrors the raw constructor btensor.h:168 + check_tensor (btensor.cpp:405-467): blocks violating the selection
+ * rule or repeated -> QTB_ERR_INVALID_ARGUMENT. */
+qtb_status qtb_tensor_create(qtb_ctx *ctx, int64_t rank, int64_t nc, const int64_t *mods, const int64_t *nsec,
+                             const int64_t *sec_sizes, const int64_t *cvals, const int64_t *sel, int64_t nblocks,
+                             const int64_t *block_index, const double *host_data, qtb_tensor **out);
+/* Zero-copy adoption of blocks that already live on the device (e.g. the data_ptr() of CUDA torch tensors held by a
+ * quantit::btensor): `block_ptr[b]` is a device pointer, `block_strides` [nblocks*rank] in elements. The memory is
+ * NOT owned; the caller keeps it alive while the handle (or any view derived from it) exists. */
+qtb_status qtb_tensor_adopt(qtb_ctx *ctx, int64_t rank, int64_t nc, const int64_t *mods, const int64_t *nsec,
+                            const int64_t *sec_sizes, const int64_t *cvals, const int64_t *sel, int64_t nblocks,
+                            const int64_t *block_index, void *const *block_ptr, const int64_t *block_strides,
+                            qtb_tensor **out);
+void qtb_tensor_free(qtb_tensor *t);
+
+/* structure queries (btensor::dim :276, section_numbers :289, section_sizes :215, get_cvals :292, selection_rule) */
+int64_t qtb_tensor_rank(const qtb_tensor *t);
+int64_t qtb_tensor_nc(const qtb_tensor *t);
+int64_t qtb_tensor_nblocks(const qtb_tensor *t);
+int64_t qtb_tensor_total_sections(const qtb_tensor *t);
+int64_t qtb_tensor_numel(const qtb_tensor *t); /* stored elements */
+qtb_status qtb_tensor_structure(const qtb_tensor *t, int64_t *nsec, int64_t *sec_sizes, int64_t *cvals, int64_t *sel,
+                                int64_t *mods);
+/* block table in block order: index [nb*rank], dims [nb*rank], strides [nb*rank] (elements), device pointers [nb].
+ * Any output pointer may be NULL. */
+qtb_status qtb_tensor_blocks(const qtb_tensor *t, int64_t *index, int64_t *dims, int64_t *strides, void **ptrs);
+/* blocks back to back in block order, each C-contiguous (strided views are gathered on the device first) */
+qtb_status qtb_tensor_download(qtb_ctx *ctx, const qtb_tensor *t, double *host_out);
+
+/* ---- structural views (no data movement; the copy the reference pays later in permute_bl is fused into the GEMM
+ *      operand load) ------------------------------------------------------------------------------------------ */
+/* btensor::permute, btensor.cpp:1754-1802 */
+qtb_status qtb_permute(qtb_ctx *ctx, const qtb_tensor *a, const int64_t *perm, qtb_tensor **out);
+/* btensor::conj for real dtypes = inverse_cvals, btensor.cpp:2156-2172 */
+qtb_status qtb_conj(qtb_ctx *ctx, const qtb_tensor *a, qtb_tensor **out);
+
+/* ---- contraction (replaces btensor::tensordot, btensor.h:623, btensor.cpp:1971-2119) ------------------------ */
+qtb_status qtb_tensordot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, int64_t k, const int64_t *dims_a,
+                         const int64_t *dims_b, qtb_tensor **out);
+/* plan only: number of output blocks, matched pairs and algorithmic flops (sum over pairs of 2*m*n*k) */
+qtb_status qtb_tensordot_plan_info(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, int64_t k,
+                                   const int64_t *dims_a, const int64_t *dims_b, int64_t *n_out_blocks,
+                                   int64_t *n_pairs, int64_t *flops);
+/* re-run a contraction into an existing output of identical layout (benchmark loops; no allocation) */
+qtb_status qtb_tensordot_into(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, int64_t k,
+                              const int64_t *dims_a, const int64_t *dims_b, qtb_tensor *out);
+/* One call from host buffers to host buffers (upload A,B; contract; download C). `c_index`/`c_data` may be NULL to
+ * query sizes first (n_out_blocks, c_numel). This is the end-to-end entry the reference-side adaptor uses for CPU
+ * btensors. */
+qtb_status qtb_tensordot_host(qtb_ctx *ctx, int64_t nc, const int64_t *mods,
+                              int64_t rank_a, const int64_t *nsec_a, const int64_t *sec_sizes_a, const int64_t *cvals_a,
+                              const int64_t *sel_a, int64_t nblocks_a, const int64_t *index_a, const double *data_a,
+                              int64_t rank_b, const int64_t *nsec_b, const int64_t *sec_sizes_b, const int64_t *cvals_b,
+                              const int64_t *sel_b, int64_t nblocks_b, const int64_t *index_b, const double *data_b,
+                              int64_t k, const int64_t *dims_a, const int64_t *dims_b,
+                              int64_t *n_out_blocks, int64_t *c_numel, int64_t *c_index, double *c_data);
+
+/* ---- elementwise / Lanczos vector ops (replace btensor mul/add_/div_/sum/sqrt, btensor.cpp:895-976,1204-1302,
+ *      1499-1621,2666-2752 as used by dmrg.cpp:585-638) ------------------------------------------------------- */
+/* out = alpha*a + beta*b with the union of the two block lists (btensor::add, btensor.cpp:2666-2752) */
+qtb_status qtb_axpby(qtb_ctx *ctx, double alpha, const qtb_tensor *a, double beta, const qtb_tensor *b,
+                     qtb_tensor **out);
+/* <a,b> = tensordot over every index (dmrg.cpp:593): result written to *host_out (one device->host sync) */
+qtb_status qtb_dot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double *host_out);
+/* a *= s in place */
+qtb_status qtb_scale_(qtb_ctx *ctx, qtb_tensor *a, double s);
+/* out(…,k) = a(…,k) * d(k), d rank-1 over a's last dim; blocks with no partner in d are dropped
+ * (btensor::mul_ broadcast, btensor.cpp:1204-1302 as used at dmrg.cpp:192,198) */
+qtb_status qtb_mul_lastdim(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *d, qtb_tensor **out);
+
+/* ---- block SVD + truncation (replaces quantit::svd(btensor, split, tol, min, max, pow),
+ *      blockTensor/LinearAlgebra.h:115, btensor_linalg.cpp:390-534,657-755,805-809; compute_last_index
+ *      LinearAlgebra.cpp:57-75) -------------------------------------------------------------------------------- */
+/* truncate = 0: plain svd(A, split). max_size < 0 means "no maximum" (SIZE_MAX in the reference). */
+qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncate, double tol, int64_t min_size,
+                   int64_t max_size, double pow, qtb_tensor **u, qtb_tensor **d, qtb_tensor **v);
+
+/* ---- two-site DMRG pieces (dmrg.cpp) ----------------------------------------------------------------------- */
+/* details::hamil2site_times_state, dmrg.cpp:520-531 */
+qtb_status qtb_heff_apply(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
+                          const qtb_tensor *renv, qtb_tensor **out);
+/* compute_left_env / compute_right_env, dmrg.cpp:424-493 */
+qtb_status qtb_env_left(qtb_ctx *ctx, const qtb_tensor *h, const qtb_tensor *mps, const qtb_tensor *lenv,
+                        qtb_tensor **out);
+qtb_status qtb_env_right(qtb_ctx *ctx, const qtb_tensor *h, const qtb_tensor *mps, const qtb_tensor *renv,
+                         qtb_tensor **out);
+/* two_sites_update = one_step_lanczos + eig2x2Mat + recombination, dmrg.cpp:543-651. */
+qtb_status qtb_two_sites_update(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
+                                const qtb_tensor *renv, double *energy, qtb_tensor **psi_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTB_H */

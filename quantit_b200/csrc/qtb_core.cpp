@@ -1,0 +1,871 @@
+// qtb_core.cpp — context, arenas, block tables, structural views, the contraction planner and tensordot.
+#include "qtb_core.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+#include "qtb_vec.h"
+
+namespace qtb
+{
+
+// =====================================================================================================================
+// context / memory
+// =====================================================================================================================
+Ctx::~Ctx()
+{
+	plan_cache.clear();
+	if (pinned)
+		cudaFreeHost(pinned);
+	if (own_stream && stream)
+		cudaStreamDestroy(stream);
+}
+
+void *Ctx::pinned_buf(size_t bytes)
+{
+	if (bytes > pinned_bytes)
+	{
+		if (pinned)
+		{
+			cudaStreamSynchronize(stream);
+			cudaFreeHost(pinned);
+		}
+		pinned_bytes = std::max<size_t>(bytes * 2, size_t(1) << 20);
+		QTB_CUDA(cudaMallocHost(&pinned, pinned_bytes));
+	}
+	return pinned;
+}
+
+void *ctx_alloc(Ctx &ctx, size_t bytes)
+{
+	void *p = nullptr;
+	if (bytes == 0)
+		bytes = 8;
+	QTB_CUDA(cudaMallocAsync(&p, bytes, ctx.stream));
+	return p;
+}
+void ctx_free(Ctx &ctx, void *p)
+{
+	if (p)
+		cudaFreeAsync(p, ctx.stream);
+}
+
+// Small structure tables go through a pinned ring so that the copy is truly asynchronous; the ring is only recycled
+// after a stream synchronisation.
+namespace
+{
+struct Ring
+{
+	char *base = nullptr;
+	size_t size = 0, pos = 0;
+};
+std::unordered_map<Ctx *, Ring> g_rings;
+} // namespace
+
+void *ctx_upload(Ctx &ctx, const void *host, size_t bytes)
+{
+	void *d = ctx_alloc(ctx, bytes);
+	if (bytes == 0)
+		return d;
+	Ring &r = g_rings[&ctx];
+	const size_t need = (bytes + 255) & ~size_t(255);
+	if (r.base == nullptr || need > r.size)
+	{
+		if (r.base)
+		{
+			cudaStreamSynchronize(ctx.stream);
+			cudaFreeHost(r.base);
+		}
+		r.size = std::max<size_t>(need * 2, size_t(16) << 20);
+		QTB_CUDA(cudaMallocHost((void **)&r.base, r.size));
+		r.pos = 0;
+	}
+	if (r.pos + need > r.size)
+	{
+		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+		r.pos = 0;
+	}
+	std::memcpy(r.base + r.pos, host, bytes);
+	QTB_CUDA(cudaMemcpyAsync(d, r.base + r.pos, bytes, cudaMemcpyHostToDevice, ctx.stream));
+	r.pos += need;
+	ctx.counters[4] += (i64)bytes;
+	return d;
+}
+void ctx_release_ring(Ctx *ctx)
+{
+	auto it = g_rings.find(ctx);
+	if (it != g_rings.end())
+	{
+		if (it->second.base)
+			cudaFreeHost(it->second.base);
+		g_rings.erase(it);
+	}
+}
+
+Arena::Arena(Ctx *c, i64 n) : numel(n), owned(true), ctx(c)
+{
+	size_t bytes = std::max<i64>(n, 1) * sizeof(double);
+	QTB_CUDA(cudaMallocAsync((void **)&ptr, bytes, c->stream));
+	c->counters[7] += (i64)bytes;
+}
+Arena::~Arena()
+{
+	if (owned && ptr)
+	{
+		cudaFreeAsync(ptr, ctx->stream);
+		ctx->counters[7] -= (i64)(std::max<i64>(numel, 1) * sizeof(double));
+	}
+}
+
+Plan::~Plan()
+{
+	if (d_blob && ctx)
+		cudaFreeAsync(d_blob, ctx->stream);
+}
+
+// =====================================================================================================================
+// structure / block tables
+// =====================================================================================================================
+void Structure::finalize()
+{
+	sec_off.assign(rank + 1, 0);
+	for (i64 d = 0; d < rank; ++d)
+		sec_off[d + 1] = sec_off[d] + nsec[d];
+}
+bool Structure::allowed(const i64 *index) const
+{
+	for (i64 c = 0; c < ct.nc; ++c)
+	{
+		i64 q = 0;
+		for (i64 d = 0; d < rank; ++d)
+			q += charge_of(d, index[d])[c];
+		if (ct.norm(q, c) != ct.norm(sel[c], c))
+			return false;
+	}
+	return true;
+}
+i64 Structure::dim_size(i64 dim) const
+{
+	i64 s = 0;
+	for (i64 k = 0; k < nsec[dim]; ++k)
+		s += size_of(dim, k);
+	return s;
+}
+
+std::vector<i64> sort_blocks(i64 rank, std::vector<i64> &index)
+{
+	const i64 nb = rank ? (i64)index.size() / rank : (index.empty() ? 0 : 0);
+	std::vector<i64> perm(nb);
+	std::iota(perm.begin(), perm.end(), 0);
+	std::stable_sort(perm.begin(), perm.end(),
+	                 [&](i64 x, i64 y)
+	                 {
+		                 return std::lexicographical_compare(index.begin() + x * rank, index.begin() + (x + 1) * rank,
+		                                                     index.begin() + y * rank, index.begin() + (y + 1) * rank);
+	                 });
+	std::vector<i64> sorted(index.size());
+	for (i64 i = 0; i < nb; ++i)
+		std::copy(index.begin() + perm[i] * rank, index.begin() + (perm[i] + 1) * rank, sorted.begin() + i * rank);
+	index.swap(sorted);
+	return perm;
+}
+
+bool Tensor::block_contiguous(i64 b) const
+{
+	i64 expect = 1;
+	for (i64 d = st.rank - 1; d >= 0; --d)
+	{
+		if (dm(b)[d] != 1 && sd(b)[d] != expect)
+			return false;
+		expect *= dm(b)[d];
+	}
+	return true;
+}
+bool Tensor::packed_canonical() const
+{
+	for (i64 b = 0; b < nblocks; ++b)
+		if (!block_contiguous(b))
+			return false;
+	return true;
+}
+static inline uint64_t mix64(uint64_t h, uint64_t v)
+{
+	h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+	h *= 0xff51afd7ed558ccdull;
+	h ^= h >> 33;
+	return h;
+}
+void Tensor::compute_hash()
+{
+	uint64_t h = 0x1234567ull;
+	h = mix64(h, (uint64_t)st.rank);
+	h = mix64(h, (uint64_t)nblocks);
+	for (auto v : st.nsec)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : st.sec_sizes)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : st.cvals)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : st.sel)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : index)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : dims)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : strides)
+		h = mix64(h, (uint64_t)v);
+	for (auto v : offs)
+		h = mix64(h, (uint64_t)v);
+	layout_hash = h;
+}
+void Tensor::dims_from_structure()
+{
+	dims.resize(nblocks * st.rank);
+	for (i64 b = 0; b < nblocks; ++b)
+		for (i64 d = 0; d < st.rank; ++d)
+			dims[b * st.rank + d] = st.size_of(d, index[b * st.rank + d]);
+}
+i64 Tensor::layout_packed()
+{
+	strides.resize(nblocks * st.rank);
+	offs.resize(nblocks);
+	i64 pos = 0;
+	for (i64 b = 0; b < nblocks; ++b)
+	{
+		i64 s = 1;
+		for (i64 d = st.rank - 1; d >= 0; --d)
+		{
+			strides[b * st.rank + d] = s;
+			s *= dims[b * st.rank + d];
+		}
+		offs[b] = pos;
+		pos += (s + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+	}
+	return pos;
+}
+i64 Tensor::find_block(const i64 *index_) const
+{
+	i64 lo = 0, hi = nblocks;
+	const i64 r = st.rank;
+	while (lo < hi)
+	{
+		i64 mid = (lo + hi) / 2;
+		if (std::lexicographical_compare(idx(mid), idx(mid) + r, index_, index_ + r))
+			lo = mid + 1;
+		else
+			hi = mid;
+	}
+	if (lo < nblocks && std::equal(idx(lo), idx(lo) + r, index_))
+		return lo;
+	return -1;
+}
+
+// =====================================================================================================================
+// creation / download
+// =====================================================================================================================
+static void check_structure(const Structure &st)
+{ // the structural half of reference check_tensor, btensor.cpp:405-467
+	QTB_REQUIRE(st.rank >= 0 && (i64)st.nsec.size() == st.rank, QTB_ERR_INVALID_ARGUMENT,
+	            "Invalid argument to construct a block tensor: rank and section table disagree");
+	QTB_REQUIRE((i64)st.sel.size() == st.ct.nc, QTB_ERR_INVALID_ARGUMENT, "selection rule has the wrong arity");
+	i64 tot = 0;
+	for (auto n : st.nsec)
+	{
+		QTB_REQUIRE(n >= 0, QTB_ERR_INVALID_ARGUMENT, "negative section count");
+		tot += n;
+	}
+	QTB_REQUIRE((i64)st.sec_sizes.size() == tot && (i64)st.cvals.size() == tot * st.ct.nc, QTB_ERR_INVALID_ARGUMENT,
+	            "Invalid argument to construct a block tensor: section sizes / conserved values length mismatch");
+	for (auto s : st.sec_sizes)
+		QTB_REQUIRE(s >= 0, QTB_ERR_INVALID_ARGUMENT, "negative section size");
+}
+
+std::unique_ptr<Tensor> make_tensor(Ctx &ctx, const Structure &st_in, i64 nblocks, const i64 *block_index,
+                                    const double *host_data)
+{
+	auto t = std::make_unique<Tensor>();
+	t->st = st_in;
+	t->st.finalize();
+	check_structure(t->st);
+	const i64 r = t->st.rank;
+	t->nblocks = nblocks;
+	t->index.assign(block_index, block_index + nblocks * r);
+	for (i64 b = 0; b < nblocks; ++b)
+	{
+		for (i64 d = 0; d < r; ++d)
+			QTB_REQUIRE(t->index[b * r + d] >= 0 && t->index[b * r + d] < t->st.nsec[d], QTB_ERR_INVALID_ARGUMENT,
+			            "block index out of the section range");
+		QTB_REQUIRE(t->st.allowed(&t->index[b * r]), QTB_ERR_INVALID_ARGUMENT,
+		            "Invalid argument to construct a block tensor: a block violates the selection rule");
+	}
+	std::vector<i64> perm;
+	if (r > 0)
+		perm = sort_blocks(r, t->index);
+	else
+	{
+		QTB_REQUIRE(nblocks <= 1, QTB_ERR_INVALID_ARGUMENT, "a rank-0 tensor holds at most one block");
+		perm.assign(nblocks, 0);
+	}
+	for (i64 b = 1; b < nblocks; ++b)
+		QTB_REQUIRE(!std::equal(t->idx(b - 1), t->idx(b - 1) + r, t->idx(b)), QTB_ERR_INVALID_ARGUMENT,
+		            "Invalid argument to construct a block tensor: repeated block index");
+	t->dims_from_structure();
+	const i64 total = t->layout_packed();
+	t->arena = std::make_shared<Arena>(&ctx, total);
+	if (total > 0)
+	{
+		if (host_data == nullptr)
+			QTB_CUDA(cudaMemsetAsync(t->arena->ptr, 0, total * sizeof(double), ctx.stream));
+		else
+		{
+			// source offsets in the GIVEN order
+			std::vector<i64> src_off(nblocks);
+			std::vector<i64> numel_given(nblocks);
+			for (i64 nb = 0; nb < nblocks; ++nb)
+				numel_given[perm[nb]] = t->block_numel(nb);
+			i64 pos = 0;
+			for (i64 g = 0; g < nblocks; ++g)
+			{
+				src_off[g] = pos;
+				pos += numel_given[g];
+			}
+			// stage the packed (aligned) image in pinned memory, one H2D copy
+			double *stage = (double *)ctx.pinned_buf(total * sizeof(double));
+			QTB_CUDA(cudaStreamSynchronize(ctx.stream)); // staging buffer may still be in flight
+			for (i64 nb = 0; nb < nblocks; ++nb)
+			{
+				const i64 n = t->block_numel(nb);
+				std::memcpy(stage + t->offs[nb], host_data + src_off[perm[nb]], n * sizeof(double));
+				const i64 padded = (n + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+				if (padded > n)
+					std::memset(stage + t->offs[nb] + n, 0, (padded - n) * sizeof(double));
+			}
+			QTB_CUDA(cudaMemcpyAsync(t->arena->ptr, stage, total * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
+			ctx.counters[4] += total * (i64)sizeof(double);
+		}
+	}
+	t->compute_hash();
+	return t;
+}
+
+std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t)
+{
+	auto out = std::make_unique<Tensor>();
+	out->st = t.st;
+	out->nblocks = t.nblocks;
+	out->index = t.index;
+	out->dims = t.dims;
+	const i64 total = out->layout_packed();
+	out->arena = std::make_shared<Arena>(&ctx, total);
+	if (total > 0)
+		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, total * sizeof(double), ctx.stream));
+	std::vector<GatherDesc> descs;
+	for (i64 b = 0; b < t.nblocks; ++b)
+	{
+		GatherDesc d{};
+		d.src_off = t.offs[b];
+		d.dst_off = out->offs[b];
+		d.numel = t.block_numel(b);
+		d.rank = (int)t.st.rank;
+		QTB_REQUIRE(d.rank <= 8, QTB_ERR_INVALID_ARGUMENT, "rank > 8 is not supported");
+		for (int k = 0; k < d.rank; ++k)
+		{
+			d.dims[k] = t.dm(b)[k];
+			d.strides[k] = t.sd(b)[k];
+		}
+		if (d.numel > 0)
+			descs.push_back(d);
+	}
+	launch_gather(ctx, descs, t.arena->ptr, out->arena->ptr);
+	out->compute_hash();
+	return out;
+}
+
+void download(Ctx &ctx, const Tensor &t, double *host_out)
+{
+	std::unique_ptr<Tensor> tmp;
+	const Tensor *src = &t;
+	if (!t.packed_canonical())
+	{
+		tmp = contiguous(ctx, t);
+		src = tmp.get();
+	}
+	// blocks may sit anywhere in the arena (views of larger arenas): copy block by block into a pinned image
+	i64 total = 0;
+	for (i64 b = 0; b < src->nblocks; ++b)
+		total += src->block_numel(b);
+	if (total == 0)
+		return;
+	QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+	double *stage = (double *)ctx.pinned_buf(total * sizeof(double));
+	i64 pos = 0;
+	for (i64 b = 0; b < src->nblocks; ++b)
+	{
+		const i64 n = src->block_numel(b);
+		if (n)
+			QTB_CUDA(cudaMemcpyAsync(stage + pos, src->arena->ptr + src->offs[b], n * sizeof(double),
+			                         cudaMemcpyDeviceToHost, ctx.stream));
+		pos += n;
+	}
+	QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+	std::memcpy(host_out, stage, total * sizeof(double));
+	ctx.counters[5] += total * (i64)sizeof(double);
+}
+
+// =====================================================================================================================
+// structural views
+// =====================================================================================================================
+std::unique_ptr<Tensor> permute(const Tensor &a, const std::vector<i64> &perm_in)
+{ // reference btensor::permute, btensor.cpp:1754-1802: metadata only, blocks keep aliasing the same storage
+	const i64 r = a.st.rank;
+	QTB_REQUIRE((i64)perm_in.size() == r, QTB_ERR_INVALID_ARGUMENT, "permutation length differs from the tensor rank");
+	std::vector<i64> perm(r);
+	std::vector<char> seen(r, 0);
+	for (i64 i = 0; i < r; ++i)
+	{
+		perm[i] = perm_in[i] < 0 ? perm_in[i] + r : perm_in[i];
+		QTB_REQUIRE(perm[i] >= 0 && perm[i] < r && !seen[perm[i]], QTB_ERR_INVALID_ARGUMENT, "invalid permutation");
+		seen[perm[i]] = 1;
+	}
+	auto out = std::make_unique<Tensor>();
+	out->st.rank = r;
+	out->st.ct = a.st.ct;
+	out->st.sel = a.st.sel;
+	out->st.nsec.resize(r);
+	for (i64 i = 0; i < r; ++i)
+	{
+		const i64 p = perm[i];
+		out->st.nsec[i] = a.st.nsec[p];
+		for (i64 s = 0; s < a.st.nsec[p]; ++s)
+		{
+			out->st.sec_sizes.push_back(a.st.size_of(p, s));
+			const i64 *c = a.st.charge_of(p, s);
+			out->st.cvals.insert(out->st.cvals.end(), c, c + a.st.ct.nc);
+		}
+	}
+	out->st.finalize();
+	out->nblocks = a.nblocks;
+	out->index.resize(a.index.size());
+	for (i64 b = 0; b < a.nblocks; ++b)
+		for (i64 i = 0; i < r; ++i)
+			out->index[b * r + i] = a.index[b * r + perm[i]];
+	std::vector<i64> order(a.nblocks);
+	if (r > 0)
+		order = sort_blocks(r, out->index);
+	else
+		std::iota(order.begin(), order.end(), 0);
+	out->dims.resize(a.dims.size());
+	out->strides.resize(a.strides.size());
+	out->offs.resize(a.nblocks);
+	for (i64 nb = 0; nb < a.nblocks; ++nb)
+	{
+		const i64 ob = order[nb];
+		for (i64 i = 0; i < r; ++i)
+		{
+			out->dims[nb * r + i] = a.dims[ob * r + perm[i]];
+			out->strides[nb * r + i] = a.strides[ob * r + perm[i]];
+		}
+		out->offs[nb] = a.offs[ob];
+	}
+	out->arena = a.arena;
+	out->compute_hash();
+	return out;
+}
+
+std::unique_ptr<Tensor> conj(const Tensor &a)
+{ // reference btensor::conj for a real dtype: conj_only() is the identity, inverse_cvals_() flips every section
+  // charge and the selection rule (btensor.cpp:2156-2172). Storage is shared.
+	auto out = std::make_unique<Tensor>(a);
+	const i64 nc = a.st.ct.nc;
+	for (size_t i = 0; i < out->st.cvals.size(); ++i)
+		out->st.cvals[i] = a.st.ct.norm(-a.st.cvals[i], (i64)(i % nc));
+	for (i64 c = 0; c < nc; ++c)
+		out->st.sel[c] = a.st.ct.norm(-a.st.sel[c], c);
+	out->compute_hash();
+	return out;
+}
+
+// =====================================================================================================================
+// contraction planner
+// =====================================================================================================================
+namespace
+{
+// int32 offsets of the C-order flattening of `dimlist` of block b (relative to the block's first element)
+std::vector<int32_t> flat_offsets(const Tensor &t, i64 b, const std::vector<i64> &dimlist)
+{
+	i64 n = 1;
+	for (auto d : dimlist)
+		n *= t.dm(b)[d];
+	std::vector<int32_t> out((size_t)n);
+	if (n == 0)
+		return out;
+	const size_t nd = dimlist.size();
+	std::vector<i64> counter(nd, 0);
+	i64 off = 0;
+	for (i64 e = 0; e < n; ++e)
+	{
+		QTB_REQUIRE(off >= 0 && off < (i64(1) << 31), QTB_ERR_INVALID_ARGUMENT, "block extent exceeds 2^31 elements");
+		out[(size_t)e] = (int32_t)off;
+		for (i64 k = (i64)nd - 1; k >= 0; --k)
+		{
+			const i64 d = dimlist[k];
+			if (++counter[k] < t.dm(b)[d])
+			{
+				off += t.sd(b)[d];
+				break;
+			}
+			off -= (counter[k] - 1) * t.sd(b)[d];
+			counter[k] = 0;
+		}
+	}
+	return out;
+}
+bool unit_stride(const std::vector<int32_t> &o)
+{
+	for (size_t i = 1; i < o.size(); ++i)
+		if (o[i] - o[i - 1] != 1)
+			return false;
+	return true;
+}
+struct Cand
+{
+	std::vector<i64> key; // [freeA..., freeB..., contracted...]
+	i64 a, b;
+};
+} // namespace
+
+static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a_in,
+                                        const std::vector<i64> &dims_b_in)
+{
+	// ---- validation: reference compute_tdot_shape + check_product_compat<true>, btensor.cpp:841-883,783-825 ----
+	QTB_REQUIRE(dims_a_in.size() == dims_b_in.size(), QTB_ERR_CHECK,
+	            "both dimension lists should have the same length.");
+	QTB_REQUIRE(a.st.ct == b.st.ct, QTB_ERR_CHECK, "the two tensors have different type of conserved quantities");
+	const i64 k = (i64)dims_a_in.size();
+	const i64 ra = a.st.rank, rb = b.st.rank;
+	std::vector<i64> dims_a(k), dims_b(k);
+	std::vector<char> ca(ra, 0), cb(rb, 0);
+	for (i64 i = 0; i < k; ++i)
+	{
+		dims_a[i] = dims_a_in[i] < 0 ? dims_a_in[i] + ra : dims_a_in[i];
+		dims_b[i] = dims_b_in[i] < 0 ? dims_b_in[i] + rb : dims_b_in[i];
+		QTB_REQUIRE(dims_a[i] >= 0 && dims_a[i] < ra && dims_b[i] >= 0 && dims_b[i] < rb, QTB_ERR_CHECK,
+		            "contracted dimension out of range");
+		QTB_REQUIRE(!ca[dims_a[i]] && !cb[dims_b[i]], QTB_ERR_CHECK, "dim appears multiple times in the list of dims");
+		ca[dims_a[i]] = cb[dims_b[i]] = 1;
+	}
+	const i64 nc = a.st.ct.nc;
+	for (i64 i = 0; i < k; ++i)
+	{
+		const i64 s1 = a.st.nsec[dims_a[i]], s2 = b.st.nsec[dims_b[i]];
+		QTB_REQUIRE(s1 == s2, QTB_ERR_CHECK,
+		            "contracted dimensions need to match, but first has " + std::to_string(s1) +
+		                " sections along dim " + std::to_string(dims_a[i]) + "  and second has " + std::to_string(s2) +
+		                " sections along dim " + std::to_string(dims_b[i]));
+		for (i64 s = 0; s < s1; ++s)
+			for (i64 c = 0; c < nc; ++c)
+				QTB_REQUIRE(a.st.ct.norm(a.st.charge_of(dims_a[i], s)[c] + b.st.charge_of(dims_b[i], s)[c], c) == 0,
+				            QTB_ERR_CHECK,
+				            "contracted conserved numbers need to sum to zero, but there is a violation when "
+				            "contracting dim " +
+				                std::to_string(dims_a[i]) + " of the left tensor with dim " +
+				                std::to_string(dims_b[i]) + " of the right tensor");
+	}
+	std::vector<i64> free_a, free_b;
+	for (i64 i = 0; i < ra; ++i)
+		if (!ca[i])
+			free_a.push_back(i);
+	for (i64 i = 0; i < rb; ++i)
+		if (!cb[i])
+			free_b.push_back(i);
+	const i64 nfa = (i64)free_a.size(), nfb = (i64)free_b.size();
+	QTB_REQUIRE(nfa + nfb <= 8, QTB_ERR_INVALID_ARGUMENT, "output rank > 8 is not supported");
+
+	auto plan = std::make_shared<Plan>();
+	plan->ctx = &ctx;
+	Tensor &out = plan->out_proto;
+	// ---- output structure: reference compute_tdot_cval_sectSize, btensor.cpp:1908-1935 ----
+	out.st.rank = nfa + nfb;
+	out.st.ct = a.st.ct;
+	out.st.sel.resize(nc);
+	for (i64 c = 0; c < nc; ++c)
+		out.st.sel[c] = a.st.ct.norm(a.st.sel[c] + b.st.sel[c], c);
+	auto push_dim = [&](const Tensor &t, i64 d)
+	{
+		out.st.nsec.push_back(t.st.nsec[d]);
+		for (i64 s = 0; s < t.st.nsec[d]; ++s)
+		{
+			out.st.sec_sizes.push_back(t.st.size_of(d, s));
+			const i64 *c = t.st.charge_of(d, s);
+			out.st.cvals.insert(out.st.cvals.end(), c, c + nc);
+		}
+	};
+	for (auto d : free_a)
+		push_dim(a, d);
+	for (auto d : free_b)
+		push_dim(b, d);
+	out.st.finalize();
+
+	// ---- block-pair matching: reference two-pointer merge over "columns", btensor.cpp:2057-2108 ----
+	// Equivalent formulation: every (A block, B block) pair with equal contracted block indices, grouped by the output
+	// index (freeA, freeB) in ascending order, pairs inside a group in ascending contracted index.
+	std::map<std::vector<i64>, std::vector<i64>> b_by_contr;
+	for (i64 j = 0; j < b.nblocks; ++j)
+	{
+		std::vector<i64> key(k);
+		for (i64 i = 0; i < k; ++i)
+			key[i] = b.idx(j)[dims_b[i]];
+		b_by_contr[key].push_back(j);
+	}
+	std::vector<Cand> cands;
+	{
+		std::vector<i64> key(k);
+		for (i64 i = 0; i < a.nblocks; ++i)
+		{
+			for (i64 c = 0; c < k; ++c)
+				key[c] = a.idx(i)[dims_a[c]];
+			auto it = b_by_contr.find(key);
+			if (it == b_by_contr.end())
+				continue;
+			for (i64 j : it->second)
+			{
+				Cand cd;
+				cd.key.reserve(nfa + nfb + k);
+				for (auto d : free_a)
+					cd.key.push_back(a.idx(i)[d]);
+				for (auto d : free_b)
+					cd.key.push_back(b.idx(j)[d]);
+				cd.key.insert(cd.key.end(), key.begin(), key.end());
+				cd.a = i;
+				cd.b = j;
+				cands.push_back(std::move(cd));
+			}
+		}
+	}
+	std::sort(cands.begin(), cands.end(), [](const Cand &x, const Cand &y) { return x.key < y.key; });
+
+	// ---- operand offset tables (the fused permute_bl, btensor.cpp:1843-1894) ----
+	struct OpTab
+	{
+		int32_t r = -1, c = -1;
+		int contig = 0;
+	};
+	std::vector<OpTab> atab(a.nblocks), btab(b.nblocks);
+	auto push_pool = [&](const std::vector<int32_t> &v)
+	{
+		const int32_t pos = (int32_t)plan->offpool.size();
+		plan->offpool.insert(plan->offpool.end(), v.begin(), v.end());
+		return pos;
+	};
+	auto a_tab = [&](i64 i) -> OpTab &
+	{
+		OpTab &t = atab[i];
+		if (t.r < 0)
+		{
+			auto ro = flat_offsets(a, i, free_a);
+			auto ko = flat_offsets(a, i, dims_a);
+			t.contig = (ko.size() > 1) ? unit_stride(ko) : !(ro.size() > 1 && unit_stride(ro));
+			t.r = push_pool(ro);
+			t.c = push_pool(ko);
+		}
+		return t;
+	};
+	auto b_tab = [&](i64 j) -> OpTab &
+	{
+		OpTab &t = btab[j];
+		if (t.r < 0)
+		{
+			auto ko = flat_offsets(b, j, dims_b);
+			auto co = flat_offsets(b, j, free_b);
+			t.contig = (co.size() > 1) ? unit_stride(co) : !(ko.size() > 1 && unit_stride(ko));
+			t.r = push_pool(ko);
+			t.c = push_pool(co);
+		}
+		return t;
+	};
+
+	// ---- group into output blocks ----
+	const i64 ro = out.st.rank;
+	bool need_zero = false;
+	size_t pos = 0;
+	std::vector<i64> Ms, Ns;
+	while (pos < cands.size())
+	{
+		size_t end = pos + 1;
+		while (end < cands.size() && std::equal(cands[pos].key.begin(), cands[pos].key.begin() + ro, cands[end].key.begin()))
+			++end;
+		out.index.insert(out.index.end(), cands[pos].key.begin(), cands[pos].key.begin() + ro);
+		GemmOut go{};
+		i64 M = 1, N = 1;
+		for (auto d : free_a)
+			M *= a.dm(cands[pos].a)[d];
+		for (auto d : free_b)
+			N *= b.dm(cands[pos].b)[d];
+		go.M = (int32_t)M;
+		go.N = (int32_t)N;
+		go.pair_begin = (int32_t)plan->pairs.size();
+		for (size_t p = pos; p < end; ++p)
+		{
+			const i64 i = cands[p].a, j = cands[p].b;
+			i64 Ka = 1, Kb = 1;
+			for (i64 c = 0; c < k; ++c)
+			{
+				Ka *= a.dm(i)[dims_a[c]];
+				Kb *= b.dm(j)[dims_b[c]];
+			}
+			// the reference surfaces a size mismatch as a torch::mm shape error (c10::Error)
+			QTB_REQUIRE(Ka == Kb, QTB_ERR_CHECK,
+			            "mat1 and mat2 shapes cannot be multiplied (contracted section sizes differ)");
+			if (Ka == 0 || M == 0 || N == 0)
+				continue;
+			GemmPair gp{};
+			gp.a_off = a.offs[i];
+			gp.b_off = b.offs[j];
+			gp.K = (int32_t)Ka;
+			OpTab &ta = a_tab(i);
+			OpTab &tb = b_tab(j);
+			gp.a_roff = ta.r;
+			gp.a_koff = ta.c;
+			gp.a_kcontig = ta.contig;
+			gp.b_koff = tb.r;
+			gp.b_coff = tb.c;
+			gp.b_ncontig = tb.contig;
+			plan->pairs.push_back(gp);
+			plan->flops += 2 * M * N * Ka;
+		}
+		go.pair_end = (int32_t)plan->pairs.size();
+		if (go.pair_end == go.pair_begin && M * N > 0)
+			need_zero = true;
+		plan->outs.push_back(go);
+		Ms.push_back(M);
+		Ns.push_back(N);
+		pos = end;
+	}
+	out.nblocks = (i64)plan->outs.size();
+	out.dims_from_structure();
+	plan->out_numel = out.layout_packed();
+	for (i64 ob = 0; ob < out.nblocks; ++ob)
+	{
+		QTB_REQUIRE(out.block_numel(ob) == Ms[ob] * Ns[ob], QTB_ERR_CHECK,
+		            "shape mismatch between the operand blocks and the output sections");
+		plan->outs[ob].c_off = out.offs[ob];
+	}
+	out.compute_hash();
+	(void)need_zero;
+
+	// ---- tiling ----
+	auto count_tiles = [&](int bm, int bn, double &padded)
+	{
+		i64 n = 0;
+		padded = 0;
+		for (auto &o : plan->outs)
+		{
+			if (o.pair_end == o.pair_begin)
+				continue;
+			i64 ksum = 0;
+			for (int p = o.pair_begin; p < o.pair_end; ++p)
+				ksum += plan->pairs[p].K;
+			const i64 tm = (o.M + bm - 1) / bm, tn = (o.N + bn - 1) / bn;
+			n += tm * tn;
+			padded += 2.0 * tm * bm * tn * bn * ksum;
+		}
+		return n;
+	};
+	double pad64 = 0, pad128 = 0;
+	const i64 n64 = count_tiles(64, 64, pad64);
+	const i64 n128 = count_tiles(128, 128, pad128);
+	(void)n64;
+	// 128x128 tiles when they fill the machine and do not waste much on block edges
+	plan->tile_cfg = (n128 >= ctx.sm_count && pad128 <= 1.25 * pad64) ? 1 : 0;
+	const int bm = plan->tile_cfg ? 128 : 64, bn = bm;
+	std::vector<std::pair<i64, GemmTile>> tl;
+	for (size_t ob = 0; ob < plan->outs.size(); ++ob)
+	{
+		auto &o = plan->outs[ob];
+		if (o.pair_end == o.pair_begin)
+			continue;
+		i64 ksum = 0;
+		for (int p = o.pair_begin; p < o.pair_end; ++p)
+			ksum += plan->pairs[p].K;
+		for (int m0 = 0; m0 < o.M; m0 += bm)
+			for (int n0 = 0; n0 < o.N; n0 += bn)
+				tl.push_back({ksum, GemmTile{(int32_t)ob, m0, n0}});
+	}
+	std::stable_sort(tl.begin(), tl.end(), [](auto &x, auto &y) { return x.first > y.first; });
+	plan->tiles.reserve(tl.size());
+	for (auto &t : tl)
+		plan->tiles.push_back(t.second);
+
+	// ---- upload ----
+	auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+	const size_t s_outs = align(plan->outs.size() * sizeof(GemmOut));
+	const size_t s_pairs = align(plan->pairs.size() * sizeof(GemmPair));
+	const size_t s_tiles = align(plan->tiles.size() * sizeof(GemmTile));
+	const size_t s_pool = align(plan->offpool.size() * sizeof(int32_t));
+	const size_t total = s_outs + s_pairs + s_tiles + s_pool + 256;
+	std::vector<char> blob(total, 0);
+	std::memcpy(blob.data(), plan->outs.data(), plan->outs.size() * sizeof(GemmOut));
+	std::memcpy(blob.data() + s_outs, plan->pairs.data(), plan->pairs.size() * sizeof(GemmPair));
+	std::memcpy(blob.data() + s_outs + s_pairs, plan->tiles.data(), plan->tiles.size() * sizeof(GemmTile));
+	std::memcpy(blob.data() + s_outs + s_pairs + s_tiles, plan->offpool.data(), plan->offpool.size() * sizeof(int32_t));
+	plan->d_blob = ctx_upload(ctx, blob.data(), total);
+	char *base = (char *)plan->d_blob;
+	plan->d_outs = (GemmOut *)base;
+	plan->d_pairs = (GemmPair *)(base + s_outs);
+	plan->d_tiles = (GemmTile *)(base + s_outs + s_pairs);
+	plan->d_offpool = (int32_t *)(base + s_outs + s_pairs + s_tiles);
+	plan->d_counter = (int *)(base + s_outs + s_pairs + s_tiles + s_pool);
+	ctx.counters[2] += 1;
+	return plan;
+}
+
+std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                               const std::vector<i64> &dims_b)
+{
+	uint64_t h = mix64(a.layout_hash, b.layout_hash * 3 + 1);
+	h = mix64(h, dims_a.size());
+	for (auto d : dims_a)
+		h = mix64(h, (uint64_t)d + 17);
+	for (auto d : dims_b)
+		h = mix64(h, (uint64_t)d + 91);
+	auto it = ctx.plan_cache.find(h);
+	if (it != ctx.plan_cache.end())
+	{
+		ctx.counters[3] += 1;
+		return it->second;
+	}
+	if (ctx.plan_cache.size() > 8192)
+		ctx.plan_cache.clear();
+	auto p = build_plan(ctx, a, b, dims_a, dims_b);
+	ctx.plan_cache[h] = p;
+	return p;
+}
+
+std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                                  const std::vector<i64> &dims_b)
+{
+	auto plan = get_plan(ctx, a, b, dims_a, dims_b);
+	auto out = std::make_unique<Tensor>(plan->out_proto);
+	out->arena = std::make_shared<Arena>(&ctx, plan->out_numel);
+	bool any_empty = false;
+	for (auto &o : plan->outs)
+		any_empty |= (o.pair_begin == o.pair_end);
+	if (any_empty && plan->out_numel)
+		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, plan->out_numel * sizeof(double), ctx.stream));
+	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr,
+	                    out->arena->ptr);
+	return out;
+}
+
+void tensordot_into(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                    const std::vector<i64> &dims_b, Tensor &out)
+{
+	auto plan = get_plan(ctx, a, b, dims_a, dims_b);
+	QTB_REQUIRE(out.layout_hash == plan->out_proto.layout_hash && out.arena && out.arena->numel >= plan->out_numel,
+	            QTB_ERR_INVALID_ARGUMENT, "tensordot_into: the output tensor does not have the planned layout");
+	launch_grouped_gemm(ctx, *plan, a.arena->ptr, b.arena->ptr, out.arena->ptr);
+}
+
+} // namespace qtb

@@ -1,0 +1,230 @@
+// qtb_core.h — host-side data model of the engine: packed block tensors living in one device arena.
+//
+// Replaces the storage of quantit::btensor (reference include/blockTensor/btensor.h:105-110,821-837: a sorted vector
+// of (block_index, torch::Tensor) pairs, one heap tensor per block) by
+//   * ONE device allocation ("arena") per tensor, shared (ref-counted) between a tensor and its permute/conj views;
+//   * a host block table {index[rank], dims[rank], strides[rank], offset} sorted lexicographically by index
+//     (reference flat_map.h:31,151), so permute/conj are metadata-only exactly like the torch views the reference
+//     creates (btensor.cpp:1781-1782, 2156-2172) and the copy is fused into the next contraction's operand load.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/qtb.h"
+
+namespace qtb
+{
+using i64 = int64_t;
+
+// ---- errors: C++ exceptions inside the library, translated to qtb_status at the ABI ------------------------------
+struct Error : std::runtime_error
+{
+	qtb_status code;
+	Error(qtb_status c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+#define QTB_CUDA(call)                                                                                                 \
+	do                                                                                                                 \
+	{                                                                                                                  \
+		cudaError_t e__ = (call);                                                                                      \
+		if (e__ != cudaSuccess)                                                                                        \
+			throw ::qtb::Error(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? QTB_ERR_NO_DEVICE      \
+			                                                                                   : QTB_ERR_CUDA,         \
+			                   std::string(#call) + ": " + cudaGetErrorString(e__));                                   \
+	} while (0)
+#define QTB_REQUIRE(cond, code, msg)                                                                                   \
+	do                                                                                                                 \
+	{                                                                                                                  \
+		if (!(cond))                                                                                                   \
+			throw ::qtb::Error(code, msg);                                                                             \
+	} while (0)
+
+struct Ctx;
+
+// ---- device arena ------------------------------------------------------------------------------------------------
+struct Arena
+{
+	double *ptr = nullptr;
+	i64 numel = 0;
+	bool owned = true;
+	Ctx *ctx = nullptr;
+	Arena(Ctx *c, i64 n); // stream-ordered allocation from the context's pool
+	Arena(double *p) : ptr(p), owned(false) {}
+	~Arena();
+	Arena(const Arena &) = delete;
+	Arena &operator=(const Arena &) = delete;
+};
+
+// ---- charges -----------------------------------------------------------------------------------------------------
+// nc-component integer tuples stored flat; mods[c]==0 -> Z (int16 in the reference), N -> C<N>.
+struct ChargeType
+{
+	i64 nc = 0;
+	std::vector<i64> mods;
+	bool operator==(const ChargeType &o) const { return nc == o.nc && mods == o.mods; }
+	i64 norm(i64 v, i64 c) const
+	{
+		i64 m = mods[c];
+		if (m == 0)
+			return v;
+		v %= m;
+		return v < 0 ? v + m : v;
+	}
+};
+
+// ---- structure (what the reference calls the "shape" of a btensor) ------------------------------------------------
+struct Structure
+{
+	i64 rank = 0;
+	ChargeType ct;
+	std::vector<i64> nsec;      // [rank]
+	std::vector<i64> sec_off;   // [rank+1] prefix sums of nsec
+	std::vector<i64> sec_sizes; // [sum nsec]
+	std::vector<i64> cvals;     // [sum nsec * nc]
+	std::vector<i64> sel;       // [nc]
+
+	void finalize(); // builds sec_off
+	i64 total_sections() const { return sec_off.empty() ? 0 : sec_off.back(); }
+	i64 size_of(i64 dim, i64 sec) const { return sec_sizes[sec_off[dim] + sec]; }
+	const i64 *charge_of(i64 dim, i64 sec) const { return &cvals[(sec_off[dim] + sec) * ct.nc]; }
+	bool allowed(const i64 *index) const; // block_conservation_rule_test, btensor.cpp:333-345
+	i64 dim_size(i64 dim) const;
+};
+
+struct Block
+{
+	i64 off = 0;    // element offset of the block's first element from the arena base
+	i64 tab = 0;    // position of index/dims/strides in the flat tables (= block number * rank)
+};
+
+// ---- tensor ------------------------------------------------------------------------------------------------------
+struct Tensor
+{
+	Structure st;
+	i64 nblocks = 0;
+	std::vector<i64> index;   // [nblocks*rank] sorted lexicographically
+	std::vector<i64> dims;    // [nblocks*rank]
+	std::vector<i64> strides; // [nblocks*rank] in elements
+	std::vector<i64> offs;    // [nblocks] element offsets from arena->ptr
+	std::shared_ptr<Arena> arena;
+	uint64_t layout_hash = 0; // structure-only identity (index/dims/strides/offs): the plan-cache key component
+
+	i64 rank() const { return st.rank; }
+	const i64 *idx(i64 b) const { return &index[b * st.rank]; }
+	const i64 *dm(i64 b) const { return &dims[b * st.rank]; }
+	const i64 *sd(i64 b) const { return &strides[b * st.rank]; }
+	i64 block_numel(i64 b) const
+	{
+		i64 n = 1;
+		for (i64 d = 0; d < st.rank; ++d)
+			n *= dims[b * st.rank + d];
+		return n;
+	}
+	i64 numel() const
+	{
+		i64 n = 0;
+		for (i64 b = 0; b < nblocks; ++b)
+			n += block_numel(b);
+		return n;
+	}
+	bool block_contiguous(i64 b) const;
+	bool packed_canonical() const; // every block C-contiguous (the layout produced by allocate_packed)
+	void compute_hash();
+	// lay the blocks out back to back (each start aligned to 16 elements = 128 B), C-contiguous; fills strides/offs and
+	// returns the arena size in elements. dims must be set.
+	i64 layout_packed();
+	void dims_from_structure(); // dims[b] = section sizes of index[b]
+	i64 find_block(const i64 *index_) const; // -1 if absent
+};
+
+constexpr i64 kBlockAlign = 16; // elements (128 bytes): every packed block starts on a 128-byte line
+
+// sorts blocks lexicographically; returns the permutation applied (new position -> old position)
+std::vector<i64> sort_blocks(i64 rank, std::vector<i64> &index);
+
+// ---- contraction plan ----------------------------------------------------------------------------------------------
+struct GemmTile
+{
+	int32_t out_blk; // which output block
+	int32_t m0, n0;  // tile origin inside the block matrix
+};
+struct GemmOut
+{
+	i64 c_off;       // element offset of the output block in the C arena
+	int32_t M, N;    // matrix dims of the output block
+	int32_t pair_begin, pair_end;
+};
+struct GemmPair
+{
+	i64 a_off, b_off;        // element offsets of the operand blocks in their arenas
+	int32_t K;               // contracted extent
+	int32_t a_roff, a_koff;  // positions in the int32 offset pool: row offsets [M], k offsets [K] of the A block
+	int32_t b_koff, b_coff;  // k offsets [K], column offsets [N] of the B block
+	int32_t a_kcontig;       // 1: k is the unit-stride direction of A (else rows are)
+	int32_t b_ncontig;       // 1: n is the unit-stride direction of B (else k is)
+};
+
+struct Plan
+{
+	// output layout
+	Tensor out_proto; // structure + block table + packed layout, no arena
+	i64 out_numel = 0;
+	// work
+	std::vector<GemmOut> outs;
+	std::vector<GemmPair> pairs;
+	std::vector<GemmTile> tiles; // sorted by decreasing cost
+	std::vector<int32_t> offpool;
+	i64 flops = 0;
+	int tile_cfg = 0; // 0: 64x64 tiles, 1: 128x128 tiles
+	// device copies
+	void *d_blob = nullptr;
+	GemmOut *d_outs = nullptr;
+	GemmPair *d_pairs = nullptr;
+	GemmTile *d_tiles = nullptr;
+	int32_t *d_offpool = nullptr;
+	int *d_counter = nullptr;
+	Ctx *ctx = nullptr;
+	~Plan();
+};
+
+// ---- context -------------------------------------------------------------------------------------------------------
+struct Ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	cudaMemPool_t pool = nullptr;
+	int sm_count = 148;
+	i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	std::unordered_map<uint64_t, std::shared_ptr<Plan>> plan_cache;
+	// pinned staging for plan uploads / small downloads
+	void *pinned = nullptr;
+	size_t pinned_bytes = 0;
+	void *pinned_buf(size_t bytes);
+	~Ctx();
+};
+
+// ---- ops (host orchestration; kernels in the .cu files) --------------------------------------------------------------
+std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                               const std::vector<i64> &dims_b);
+std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                                  const std::vector<i64> &dims_b);
+void tensordot_into(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
+                    const std::vector<i64> &dims_b, Tensor &out);
+std::unique_ptr<Tensor> permute(const Tensor &a, const std::vector<i64> &perm);
+std::unique_ptr<Tensor> conj(const Tensor &a);
+std::unique_ptr<Tensor> make_tensor(Ctx &ctx, const Structure &st, i64 nblocks, const i64 *block_index,
+                                    const double *host_data);
+void download(Ctx &ctx, const Tensor &t, double *host_out);
+std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t); // packed copy (gathers strided views)
+
+// kernels (qtb_gemm.cu / qtb_vec.cu)
+void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c);
+void launch_gather_blocks(Ctx &ctx, const Tensor &src, double *dst_packed, const std::vector<i64> &dst_offs);
+
+} // namespace qtb

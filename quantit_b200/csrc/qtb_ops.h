@@ -1,0 +1,25 @@
+// qtb_ops.h — block-tensor vector ops and two-site DMRG pieces (qtb_ops.cpp), block SVD (qtb_svd.cu)
+#pragma once
+#include <memory>
+
+#include "qtb_core.h"
+#include "qtb_vec.h"
+
+namespace qtb
+{
+// out = (ca)*a + (cb)*b over the union of the block lists; coefficients = (*ptr or 1) * mul, read on the device.
+// divide_a: a's term is a / ca instead of ca * a.
+std::unique_ptr<Tensor> axpby_dev(Ctx &ctx, const double *ca_ptr, double ca_mul, const Tensor &a,
+                                  const double *cb_ptr, double cb_mul, const Tensor &b, bool divide_a);
+void dot_dev(Ctx &ctx, const Tensor &a, const Tensor &b, double *d_result, bool take_sqrt);
+std::unique_ptr<Tensor> mul_lastdim(Ctx &ctx, const Tensor &a, const Tensor &d);
+std::unique_ptr<Tensor> heff_apply(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,
+                                   const Tensor &renv);
+std::unique_ptr<Tensor> env_left(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &lenv);
+std::unique_ptr<Tensor> env_right(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &renv);
+std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,
+                                         const Tensor &renv, double *energy);
+// qtb_svd.cu
+void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size,
+               double pow, std::unique_ptr<Tensor> &u, std::unique_ptr<Tensor> &d, std::unique_ptr<Tensor> &v);
+} // namespace qtb

@@ -1,0 +1,448 @@
+"""ctypes binding of libqtb.so (include/qtb.h) and the host-side mirror of the reference's btensor interface.
+
+The class/method names follow the reference's public API for the hot path (reference include/blockTensor/btensor.h,
+include/blockTensor/LinearAlgebra.h, include/dmrg.h) so that parity tests read like the reference's own tests:
+`BTensor.tensordot`, `.permute`, `.conj`, `svd(t, split, tol, min, max, pow)`, `hamil2site_times_state`, ...
+
+There is NO CPU fallback: if libqtb.so is missing or no CUDA device is usable, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqtb.so")
+
+i64 = C.c_int64
+p_i64 = C.POINTER(C.c_int64)
+p_f64 = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class QtbError(RuntimeError):
+    """Base class; subclasses mirror the exception types the reference throws."""
+
+    status = 0
+
+
+class InvalidArgument(QtbError, ValueError):  # std::invalid_argument
+    status = 1
+
+
+class OutOfRange(QtbError, IndexError):  # std::out_of_range
+    status = 2
+
+
+class DomainError(QtbError):  # std::domain_error
+    status = 3
+
+
+class LogicError(QtbError):  # std::logic_error
+    status = 4
+
+
+class EngineRuntimeError(QtbError):  # std::runtime_error
+    status = 5
+
+
+class CheckError(QtbError):  # c10::Error raised by TORCH_CHECK in the reference
+    status = 6
+
+
+class CudaError(QtbError):
+    status = 7
+
+
+class NoDeviceError(QtbError):
+    status = 8
+
+
+_STATUS = {c.status: c for c in (InvalidArgument, OutOfRange, DomainError, LogicError, EngineRuntimeError, CheckError,
+                                 CudaError, NoDeviceError)}
+
+# every symbol include/qtb.h declares: (name, restype, argtypes)
+_SIGS = [
+    ("qtb_last_error", C.c_char_p, []),
+    ("qtb_version", C.c_char_p, []),
+    ("qtb_ctx_create", C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+    ("qtb_ctx_destroy", None, [vp]),
+    ("qtb_ctx_sync", C.c_int, [vp]),
+    ("qtb_ctx_stream", vp, [vp]),
+    ("qtb_ctx_counters", C.c_int, [vp, p_i64]),
+    ("qtb_tensor_create", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64, C.POINTER(vp)]),
+    ("qtb_tensor_adopt", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, C.POINTER(vp), p_i64,
+                                   C.POINTER(vp)]),
+    ("qtb_tensor_free", None, [vp]),
+    ("qtb_tensor_rank", i64, [vp]),
+    ("qtb_tensor_nc", i64, [vp]),
+    ("qtb_tensor_nblocks", i64, [vp]),
+    ("qtb_tensor_total_sections", i64, [vp]),
+    ("qtb_tensor_numel", i64, [vp]),
+    ("qtb_tensor_structure", C.c_int, [vp, p_i64, p_i64, p_i64, p_i64, p_i64]),
+    ("qtb_tensor_blocks", C.c_int, [vp, p_i64, p_i64, p_i64, C.POINTER(vp)]),
+    ("qtb_tensor_download", C.c_int, [vp, vp, p_f64]),
+    ("qtb_permute", C.c_int, [vp, vp, p_i64, C.POINTER(vp)]),
+    ("qtb_conj", C.c_int, [vp, vp, C.POINTER(vp)]),
+    ("qtb_tensordot", C.c_int, [vp, vp, vp, i64, p_i64, p_i64, C.POINTER(vp)]),
+    ("qtb_tensordot_plan_info", C.c_int, [vp, vp, vp, i64, p_i64, p_i64, p_i64, p_i64, p_i64]),
+    ("qtb_tensordot_into", C.c_int, [vp, vp, vp, i64, p_i64, p_i64, vp]),
+    ("qtb_tensordot_host", C.c_int, [vp, i64, p_i64,
+                                     i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64,
+                                     i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64,
+                                     i64, p_i64, p_i64, p_i64, p_i64, p_i64, p_f64]),
+    ("qtb_axpby", C.c_int, [vp, C.c_double, vp, C.c_double, vp, C.POINTER(vp)]),
+    ("qtb_dot", C.c_int, [vp, vp, vp, p_f64]),
+    ("qtb_scale_", C.c_int, [vp, vp, C.c_double]),
+    ("qtb_mul_lastdim", C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+    ("qtb_svd", C.c_int, [vp, vp, i64, C.c_int, C.c_double, i64, i64, C.c_double, C.POINTER(vp), C.POINTER(vp),
+                          C.POINTER(vp)]),
+    ("qtb_heff_apply", C.c_int, [vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    ("qtb_env_left", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
+    ("qtb_env_right", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
+    ("qtb_two_sites_update", C.c_int, [vp, vp, vp, vp, vp, p_f64, C.POINTER(vp)]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libqtb.so (built in-tree by __graft_entry__.build()). Loading needs no GPU; computing does."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                              "quantit_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in _SIGS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(st: int) -> None:
+    if st != 0:
+        msg = load_library().qtb_last_error().decode()
+        raise _STATUS.get(st, QtbError)(msg)
+
+
+def _arr(x, dtype=np.int64):
+    a = np.ascontiguousarray(np.asarray(x, dtype=dtype).reshape(-1))
+    return a
+
+
+def _pi(a: np.ndarray):
+    return a.ctypes.data_as(p_i64)
+
+
+def _pf(a: np.ndarray):
+    return a.ctypes.data_as(p_f64)
+
+
+class Context:
+    """One engine context = one CUDA device + stream + memory pool + plan cache (qtb_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        h = vp()
+        _check(self.lib.qtb_ctx_create(int(device), vp(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def sync(self) -> None:
+        _check(self.lib.qtb_ctx_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.qtb_ctx_stream(self.h) or 0)
+
+    def counters(self) -> Dict[str, int]:
+        out = (C.c_int64 * 8)()
+        _check(self.lib.qtb_ctx_counters(self.h, out))
+        names = ["kernel_launches", "gemm_launches", "plans_built", "plan_cache_hits", "h2d_bytes", "d2h_bytes",
+                 "gemm_flops", "device_bytes"]
+        return dict(zip(names, [int(v) for v in out]))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.qtb_ctx_destroy(self.h)
+            self.h = None
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+class BTensor:
+    """Device-resident block tensor (mirror of quantit::btensor for the hot path)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.qtb_tensor_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    # ---- construction ---------------------------------------------------------------------------------------------
+    @classmethod
+    def from_host(cls, sec_sizes: Sequence[Sequence[int]], cvals: Sequence[Sequence[Tuple[int, ...]]],
+                  sel: Tuple[int, ...], blocks: Dict[Tuple[int, ...], np.ndarray], mods: Optional[Sequence[int]] = None,
+                  ctx: Optional[Context] = None) -> "BTensor":
+        ctx = ctx or default_context()
+        rank = len(sec_sizes)
+        nc = len(sel)
+        nsec = _arr([len(s) for s in sec_sizes])
+        ss = _arr([x for s in sec_sizes for x in s])
+        cv = _arr([c for cs in cvals for q in cs for c in q])
+        sl = _arr(sel)
+        md = _arr(mods) if mods is not None else None
+        keys = list(blocks.keys())
+        idx = _arr([i for k in keys for i in k])
+        for k in keys:
+            want = tuple(sec_sizes[d][i] for d, i in enumerate(k))
+            if tuple(blocks[k].shape) != want:
+                raise InvalidArgument(f"block {k} has shape {blocks[k].shape}, sections say {want}")
+        data = (np.concatenate([np.ascontiguousarray(blocks[k], dtype=np.float64).reshape(-1) for k in keys])
+                if keys else np.zeros(0))
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        h = vp()
+        _check(ctx.lib.qtb_tensor_create(ctx.h, rank, nc, _pi(md) if md is not None else None, _pi(nsec), _pi(ss),
+                                         _pi(cv), _pi(sl), len(keys), _pi(idx), _pf(data) if data.size else None,
+                                         C.byref(h)))
+        return cls(ctx, h)
+
+    # ---- structure queries ----------------------------------------------------------------------------------------
+    def dim(self) -> int:
+        return int(self.ctx.lib.qtb_tensor_rank(self.h))
+
+    @property
+    def rank(self) -> int:
+        return self.dim()
+
+    @property
+    def nblocks(self) -> int:
+        return int(self.ctx.lib.qtb_tensor_nblocks(self.h))
+
+    def numel(self) -> int:
+        return int(self.ctx.lib.qtb_tensor_numel(self.h))
+
+    def structure(self):
+        """(sec_sizes per dim, cvals per dim, sel, mods)"""
+        lib = self.ctx.lib
+        r, nc = self.dim(), int(lib.qtb_tensor_nc(self.h))
+        tot = int(lib.qtb_tensor_total_sections(self.h))
+        nsec = np.zeros(max(r, 1), np.int64)
+        ss = np.zeros(max(tot, 1), np.int64)
+        cv = np.zeros(max(tot * nc, 1), np.int64)
+        sl = np.zeros(nc, np.int64)
+        md = np.zeros(nc, np.int64)
+        _check(lib.qtb_tensor_structure(self.h, _pi(nsec), _pi(ss), _pi(cv), _pi(sl), _pi(md)))
+        sec_sizes, cvals, k = [], [], 0
+        for d in range(r):
+            n = int(nsec[d])
+            sec_sizes.append([int(x) for x in ss[k:k + n]])
+            cvals.append([tuple(int(x) for x in cv[(k + s) * nc:(k + s + 1) * nc]) for s in range(n)])
+            k += n
+        return sec_sizes, cvals, tuple(int(x) for x in sl), tuple(int(x) for x in md)
+
+    def section_numbers(self) -> List[int]:
+        return [len(s) for s in self.structure()[0]]
+
+    def sizes(self) -> List[int]:
+        return [sum(s) for s in self.structure()[0]]
+
+    @property
+    def selection_rule(self) -> Tuple[int, ...]:
+        return self.structure()[2]
+
+    def block_table(self):
+        """(index [nb][rank], dims [nb][rank], strides [nb][rank], device pointers [nb])"""
+        r, nb = self.dim(), self.nblocks
+        idx = np.zeros(max(nb * r, 1), np.int64)
+        dims = np.zeros(max(nb * r, 1), np.int64)
+        st = np.zeros(max(nb * r, 1), np.int64)
+        ptrs = (vp * max(nb, 1))()
+        _check(self.ctx.lib.qtb_tensor_blocks(self.h, _pi(idx), _pi(dims), _pi(st), ptrs))
+        rs = lambda a: [tuple(int(x) for x in a[b * r:(b + 1) * r]) for b in range(nb)]
+        return rs(idx), rs(dims), rs(st), [int(ptrs[b] or 0) for b in range(nb)]
+
+    def block_indices(self) -> List[Tuple[int, ...]]:
+        return self.block_table()[0]
+
+    def to_host(self) -> Dict[Tuple[int, ...], np.ndarray]:
+        """blocks as C-contiguous numpy arrays (one device->host copy of the packed arena)"""
+        idx, dims, _, _ = self.block_table()
+        n = self.numel()
+        buf = np.zeros(max(n, 1), np.float64)
+        _check(self.ctx.lib.qtb_tensor_download(self.ctx.h, self.h, _pf(buf)))
+        out, pos = {}, 0
+        for i, d in zip(idx, dims):
+            m = int(np.prod(d)) if len(d) else 1
+            out[i] = buf[pos:pos + m].reshape(d).copy()
+            pos += m
+        return out
+
+    def item(self) -> float:
+        blocks = self.to_host()
+        if not blocks:
+            return 0.0
+        return float(next(iter(blocks.values())).reshape(-1)[0])
+
+    # ---- ops (reference btensor.h:623 tensordot, btensor.cpp:1754 permute, :2156 conj) -------------------------------
+    def tensordot(self, other: "BTensor", dims_self: Sequence[int], dims_other: Sequence[int]) -> "BTensor":
+        if len(dims_self) != len(dims_other):
+            raise CheckError("both dimension lists should have the same length.")
+        da, db = _arr(dims_self), _arr(dims_other)
+        h = vp()
+        _check(self.ctx.lib.qtb_tensordot(self.ctx.h, self.h, other.h, len(da), _pi(da), _pi(db), C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def tensordot_(self, other: "BTensor", dims_self, dims_other, out: "BTensor") -> "BTensor":
+        da, db = _arr(dims_self), _arr(dims_other)
+        _check(self.ctx.lib.qtb_tensordot_into(self.ctx.h, self.h, other.h, len(da), _pi(da), _pi(db), out.h))
+        return out
+
+    def tensordot_info(self, other: "BTensor", dims_self, dims_other) -> Dict[str, int]:
+        da, db = _arr(dims_self), _arr(dims_other)
+        a, b, c = i64(), i64(), i64()
+        _check(self.ctx.lib.qtb_tensordot_plan_info(self.ctx.h, self.h, other.h, len(da), _pi(da), _pi(db),
+                                                    C.byref(a), C.byref(b), C.byref(c)))
+        return {"out_blocks": a.value, "pairs": b.value, "flops": c.value}
+
+    def permute(self, perm: Sequence[int]) -> "BTensor":
+        p = _arr(perm)
+        if len(p) != self.dim():
+            raise InvalidArgument("permutation length differs from the tensor rank")
+        h = vp()
+        _check(self.ctx.lib.qtb_permute(self.ctx.h, self.h, _pi(p), C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def conj(self) -> "BTensor":
+        h = vp()
+        _check(self.ctx.lib.qtb_conj(self.ctx.h, self.h, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def add(self, other: "BTensor", alpha: float = 1.0) -> "BTensor":
+        h = vp()
+        _check(self.ctx.lib.qtb_axpby(self.ctx.h, 1.0, self.h, float(alpha), other.h, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def axpby(self, alpha: float, other: "BTensor", beta: float) -> "BTensor":
+        h = vp()
+        _check(self.ctx.lib.qtb_axpby(self.ctx.h, float(alpha), self.h, float(beta), other.h, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def dot(self, other: "BTensor") -> float:
+        out = C.c_double()
+        _check(self.ctx.lib.qtb_dot(self.ctx.h, self.h, other.h, C.byref(out)))
+        return out.value
+
+    def mul_(self, s: float) -> "BTensor":
+        _check(self.ctx.lib.qtb_scale_(self.ctx.h, self.h, float(s)))
+        return self
+
+    def mul_lastdim(self, d: "BTensor") -> "BTensor":
+        h = vp()
+        _check(self.ctx.lib.qtb_mul_lastdim(self.ctx.h, self.h, d.h, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+
+def tensordot(a: BTensor, b: BTensor, dims_a, dims_b) -> BTensor:
+    """free function, reference btensor.h:1230"""
+    return a.tensordot(b, dims_a, dims_b)
+
+
+def svd(a: BTensor, split: int, tol: Optional[float] = None, min_size: int = 1, max_size: Optional[int] = None,
+        pow: float = 2.0):
+    """reference quantit::svd(btensor, split) / (…, tol, min, max, pow), blockTensor/LinearAlgebra.h:87,115,142"""
+    hu, hd, hv = vp(), vp(), vp()
+    trunc = tol is not None
+    _check(a.ctx.lib.qtb_svd(a.ctx.h, a.h, int(split), 1 if trunc else 0, float(tol or 0.0), int(min_size),
+                             -1 if max_size is None else int(max_size), float(pow), C.byref(hu), C.byref(hd),
+                             C.byref(hv)))
+    return BTensor(a.ctx, hu), BTensor(a.ctx, hd), BTensor(a.ctx, hv)
+
+
+def hamil2site_times_state(state: BTensor, hamil: BTensor, lenv: BTensor, renv: BTensor) -> BTensor:
+    """reference details::hamil2site_times_state, dmrg.h:61, dmrg.cpp:520"""
+    h = vp()
+    _check(state.ctx.lib.qtb_heff_apply(state.ctx.h, state.h, hamil.h, lenv.h, renv.h, C.byref(h)))
+    return BTensor(state.ctx, h)
+
+
+def compute_left_env(hamil: BTensor, mps: BTensor, left_env: BTensor) -> BTensor:
+    """reference compute_left_env, dmrg.cpp:424-459"""
+    h = vp()
+    _check(mps.ctx.lib.qtb_env_left(mps.ctx.h, hamil.h, mps.h, left_env.h, C.byref(h)))
+    return BTensor(mps.ctx, h)
+
+
+def compute_right_env(hamil: BTensor, mps: BTensor, right_env: BTensor) -> BTensor:
+    """reference compute_right_env, dmrg.cpp:468-493"""
+    h = vp()
+    _check(mps.ctx.lib.qtb_env_right(mps.ctx.h, hamil.h, mps.h, right_env.h, C.byref(h)))
+    return BTensor(mps.ctx, h)
+
+
+def two_sites_update(state: BTensor, hamil: BTensor, lenv: BTensor, renv: BTensor):
+    """reference two_sites_update, dmrg.cpp:623-651: returns (energy, updated state)"""
+    h = vp()
+    e = C.c_double()
+    _check(state.ctx.lib.qtb_two_sites_update(state.ctx.h, state.h, hamil.h, lenv.h, renv.h, C.byref(e), C.byref(h)))
+    return e.value, BTensor(state.ctx, h)
+
+
+def tensordot_host(a: dict, b: dict, dims_a, dims_b, ctx: Optional[Context] = None):
+    """End-to-end C-ABI call from host buffers to host buffers (qtb_tensordot_host): `a`/`b` are dicts with keys
+    sec_sizes, cvals, sel, blocks (and optionally mods, or prebuilt flat arrays under '_flat'). Returns
+    (block indices, flat fp64 data)."""
+    ctx = ctx or default_context()
+    fa, fb = flatten_host(a), flatten_host(b)
+    da, db = _arr(dims_a), _arr(dims_b)
+    nob, numel = i64(), i64()
+    args = [ctx.h, fa["nc"], _pi(fa["mods"]) if fa["mods"] is not None else None,
+            fa["rank"], _pi(fa["nsec"]), _pi(fa["ss"]), _pi(fa["cv"]), _pi(fa["sel"]), fa["nb"], _pi(fa["idx"]), _pf(fa["data"]),
+            fb["rank"], _pi(fb["nsec"]), _pi(fb["ss"]), _pi(fb["cv"]), _pi(fb["sel"]), fb["nb"], _pi(fb["idx"]), _pf(fb["data"]),
+            len(da), _pi(da), _pi(db)]
+    _check(ctx.lib.qtb_tensordot_host(*args, C.byref(nob), C.byref(numel), None, None))
+    r_out = fa["rank"] + fb["rank"] - 2 * len(da)
+    cidx = np.zeros(max(nob.value * r_out, 1), np.int64)
+    cdata = np.zeros(max(numel.value, 1), np.float64)
+    _check(ctx.lib.qtb_tensordot_host(*args, C.byref(nob), C.byref(numel), _pi(cidx), _pf(cdata)))
+    return cidx[:nob.value * r_out].reshape(nob.value, r_out), cdata[:numel.value]
+
+
+def flatten_host(t: dict) -> dict:
+    """flat int64/fp64 arrays of a host block tensor description (done once, outside any timed region)"""
+    if "_flat" in t:
+        return t["_flat"]
+    keys = list(t["blocks"].keys())
+    f = {
+        "rank": len(t["sec_sizes"]), "nc": len(t["sel"]),
+        "mods": _arr(t["mods"]) if t.get("mods") is not None else None,
+        "nsec": _arr([len(s) for s in t["sec_sizes"]]),
+        "ss": _arr([x for s in t["sec_sizes"] for x in s]),
+        "cv": _arr([c for cs in t["cvals"] for q in cs for c in q]),
+        "sel": _arr(t["sel"]), "nb": len(keys), "idx": _arr([i for k in keys for i in k]),
+        "data": np.ascontiguousarray(np.concatenate([np.asarray(t["blocks"][k], np.float64).reshape(-1) for k in keys])
+                                     if keys else np.zeros(1)),
+    }
+    t["_flat"] = f
+    return f

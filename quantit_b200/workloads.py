@@ -1,0 +1,143 @@
+"""Synthetic block-sparse workloads of BASELINE.json's configs, as plain host descriptions.
+
+A host description is a dict {sec_sizes, cvals, sel, blocks}: section sizes per dim, section charges per dim (tuples of
+ints), selection rule, and {block index: C-contiguous fp64 ndarray}. It converts to the engine's BTensor with
+`BTensor.from_host(**desc)` and (in tests) to the oracle's BT with `BT(**desc)`.
+
+Values are uniform [0,1) from a seeded numpy Generator (the reference's rand_like fills blocks from the global torch
+RNG, sources/btensor.cpp:2399-2404; inputs are exchanged as explicit arrays instead of re-deriving that stream).
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+Charge = Tuple[int, ...]
+
+
+def bond(n_sec: int, D: int, sigma: float, step: int = 2):
+    """SURVEY.md §8d bond generator: sectors i with charge step*(i - n_sec//2), Gaussian weights, sizes
+    max(1, round(D*w_i/sum w)), remainder added to the centre sector so that the sizes sum to D."""
+    c = n_sec // 2
+    w = np.exp(-((np.arange(n_sec) - c) ** 2) / (2.0 * sigma * sigma))
+    sizes = np.maximum(1, np.rint(D * w / w.sum()).astype(np.int64))
+    sizes[c] += D - int(sizes.sum())
+    assert sizes[c] >= 1 and int(sizes.sum()) == D
+    charges = [(int(step * (i - c)),) for i in range(n_sec)]
+    return [int(s) for s in sizes], charges
+
+
+def conj_leg(leg):
+    sizes, charges = leg
+    return list(sizes), [tuple(-x for x in q) for q in charges]
+
+
+SPIN_HALF = ([1, 1], [(1,), (-1,)])                      # sigma of SURVEY.md §8d
+HEIS_MPO_BOND = ([1, 1, 1, 1, 1], [(0,), (-2,), (2,), (0,), (0,)])   # omega of §8d / appendix C
+
+
+def shape(legs, sel: Charge):
+    return {"sec_sizes": [list(l[0]) for l in legs], "cvals": [list(l[1]) for l in legs], "sel": tuple(sel),
+            "blocks": {}}
+
+
+def allowed_indices(desc) -> List[Tuple[int, ...]]:
+    nc = len(desc["sel"])
+    out = []
+    ranges = [range(len(s)) for s in desc["sec_sizes"]]
+    for idx in itertools.product(*ranges):
+        q = tuple(sum(desc["cvals"][d][i][c] for d, i in enumerate(idx)) for c in range(nc))
+        if q == tuple(desc["sel"]):
+            out.append(idx)
+    return out
+
+
+def rand_like(desc, rng: np.random.Generator):
+    out = dict(desc)
+    out["blocks"] = {}
+    for idx in allowed_indices(desc):
+        dims = tuple(desc["sec_sizes"][d][i] for d, i in enumerate(idx))
+        out["blocks"][idx] = rng.random(dims)
+    return out
+
+
+def tdot_pair(n_sec: int, D: int, sigma: float, seed: int = 1234):
+    """T1 / T2 of SURVEY.md §8d: A, B = rand_like(shape_from(beta, s, s, beta.conj())); C = A.tensordot(B,{3},{0})."""
+    rng = np.random.default_rng(seed)
+    beta = bond(n_sec, D, sigma, 2)
+    sh = shape([beta, SPIN_HALF, SPIN_HALF, conj_leg(beta)], (0,))
+    return rand_like(sh, rng), rand_like(sh, rng), [3], [0]
+
+
+T1 = dict(n_sec=41, D=2048, sigma=6.0)    # BASELINE.json configs[1] ("~40 sectors, total dim 2048")
+T2 = dict(n_sec=15, D=4096, sigma=1.6)    # DMRG-like sector profile at D=4096
+T2_8K = dict(n_sec=17, D=8192, sigma=1.8)
+
+
+def heisenberg_W(Jp: float = 0.25):
+    """Bulk U(1) Heisenberg MPO site W[wl, s', wr, s] of the reference (sources/models.cpp:24-57 with the conserving
+    bond charges {0,-2,2,0,0}), un-coalesced: 5 sections of size 1 on each bond."""
+    phys = SPIN_HALF
+    sh = shape([HEIS_MPO_BOND, phys, conj_leg(HEIS_MPO_BOND), conj_leg(phys)], (0,))
+    dense = np.zeros((5, 2, 5, 2))
+    ident = np.eye(2)
+    sz = np.diag([1.0, -1.0])
+    up = np.array([[0.0, 1.0], [0.0, 0.0]])   # s'=0 (charge +1), s=1 (charge -1)
+    dn = up.T
+    dense[0, :, 0, :] = ident
+    dense[1, :, 0, :] = up
+    dense[2, :, 0, :] = dn
+    dense[3, :, 0, :] = sz
+    dense[4, :, 1, :] = 2 * Jp * dn
+    dense[4, :, 2, :] = 2 * Jp * up
+    dense[4, :, 3, :] = Jp * sz
+    dense[4, :, 4, :] = ident
+    out = dict(sh)
+    out["blocks"] = {}
+    for idx in allowed_indices(sh):
+        v = dense[idx]
+        if v != 0.0:
+            out["blocks"][idx] = np.full((1, 1, 1, 1), v)
+    assert sum(float(b.sum() != 0) for b in out["blocks"].values()) == np.count_nonzero(dense)
+    return out
+
+
+def heff_set(n_sec: int, D: int, sigma: float, seed: int = 1234):
+    """T3 of SURVEY.md §8d: psi[a,s1,s2,b], left/right environments E[ket bond, MPO bond, bra bond] and the MPO site W
+    (the two-site MPO H2 is compute_2sitesHamil(W,W) = tensordot(W,W,{2},{0}).permute({0,1,3,4,2,5}), dmrg.cpp:503-515).
+    Leg charges follow the reference's generate_env construction (dmrg.cpp:370-392): L = (beta*, omega*, beta),
+    R = (beta, omega, beta*)."""
+    rng = np.random.default_rng(seed)
+    beta = bond(n_sec, D, sigma, 2)
+    psi = rand_like(shape([beta, SPIN_HALF, SPIN_HALF, conj_leg(beta)], (0,)), rng)
+    lenv = rand_like(shape([conj_leg(beta), conj_leg(HEIS_MPO_BOND), beta], (0,)), rng)
+    renv = rand_like(shape([beta, HEIS_MPO_BOND, conj_leg(beta)], (0,)), rng)
+    return psi, heisenberg_W(), lenv, renv
+
+
+def random_btensor(rng: np.random.Generator, rank: int, max_sec: int = 4, max_size: int = 5, nc: int = 1,
+                   fill: float = 0.7, legs=None, sel=None):
+    """small random block tensor for property tests: random sections/charges, a random subset of the allowed blocks"""
+    if legs is None:
+        legs = []
+        for _ in range(rank):
+            ns = int(rng.integers(1, max_sec + 1))
+            sizes = [int(x) for x in rng.integers(1, max_size + 1, ns)]
+            charges = [tuple(int(x) for x in rng.integers(-2, 3, nc)) for _ in range(ns)]
+            legs.append((sizes, charges))
+    if sel is None:
+        sel = tuple(int(x) for x in rng.integers(-1, 2, nc))
+    sh = shape(legs, sel)
+    out = dict(sh)
+    out["blocks"] = {}
+    for idx in allowed_indices(sh):
+        if rng.random() < fill:
+            dims = tuple(sh["sec_sizes"][d][i] for d, i in enumerate(idx))
+            out["blocks"][idx] = rng.standard_normal(dims)
+    return out
+
+
+def stored_bytes(desc) -> int:
+    return int(sum(b.size for b in desc["blocks"].values())) * 8
