@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — block tensordot throughput (BASELINE.json metric "block tensordot TFLOP/s (% FP64 peak)") on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload T1|T2|T2_8K]
+
+A "step" is ONE pass of the hot path over one batch of synthetic input: the contraction
+C = A.tensordot(B, {3}, {0}) of two random U(1) block-sparse rank-4 tensors. The default workload is
+BASELINE.json configs[1] literally (T1: 41 charge sectors, total bond dim 2048, fp64: 642 block GEMMs, 0.697 GFLOP);
+the DMRG-profile D=4096 contraction (T2, 69.5 GFLOP) is timed in the same run and reported under "workloads".
+
+  value  = algorithmic TFLOP/s (sum over matched block pairs of 2mnk / device time), inputs resident in HBM,
+           CUDA events on the engine's stream, L2 flushed between steps.
+  e2e    = the same metric through the reference-facing C-ABI call with HOST buffers (qtb_tensordot_host: upload A and B
+           from pinned host memory, contract, download C), host wall clock around the synchronous call.
+  roofline.peak = cuBLAS DGEMM 8192^3 measured live on the same GPU (MEASURED_PEAKS.json carries no fp64 entry).
+  cpu_baseline  = the reference's own CPU implementation (oracle/_ref/ref_harness, the unmodified reference sources
+           compiled against libtorch) on the box's host cores, same inputs.
+
+N>1 (torchrun): the contraction is an independent object per rank (weak scaling, no data-path collective); time is the
+max over ranks of the device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {"T1": dict(n_sec=41, D=2048, sigma=6.0), "T2": dict(n_sec=15, D=4096, sigma=1.6),
+             "T2_8K": dict(n_sec=17, D=8192, sigma=1.8)}
+WORKLOAD_DESC = {
+    "T1": "configs[1]: tensordot of two random U(1) block-sparse rank-4 tensors [b,s,s,b*] over one bond, 41 charge "
+          "sectors, total bond dim 2048, fp64 (642 block GEMMs)",
+    "T2": "DMRG-profile tensordot at D=4096: 15 Gaussian charge sectors (sigma 1.6), rank-4 x rank-4 over one bond, fp64",
+    "T2_8K": "DMRG-profile tensordot at D=8192: 17 charge sectors (sigma 1.8), fp64",
+}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self._halt = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dump_qtbt(desc, path):
+    """QTBT writer (format shared with oracle/ref_harness.cpp); local so that the product arm never imports oracle/"""
+    import struct
+    keys = sorted(desc["blocks"].keys())
+    with open(path, "wb") as f:
+        f.write(b"QTBT0001")
+        f.write(struct.pack("<3q", len(desc["sec_sizes"]), len(desc["sel"]), len(keys)))
+        f.write(np.asarray([len(s) for s in desc["sec_sizes"]], "<i8").tobytes())
+        for s in desc["sec_sizes"]:
+            f.write(np.asarray(s, "<i8").tobytes())
+        for c in desc["cvals"]:
+            f.write(np.asarray(c, "<i8").reshape(-1).tobytes())
+        f.write(np.asarray(desc["sel"], "<i8").tobytes())
+        for k in keys:
+            f.write(np.asarray(k, "<i8").tobytes())
+        for k in keys:
+            f.write(np.asarray(desc["blocks"][k].shape, "<i8").tobytes())
+        for k in keys:
+            f.write(np.ascontiguousarray(desc["blocks"][k], "<f8").tobytes())
+
+
+def algorithmic_flops(a, b, dims_a, dims_b):
+    free_a = [i for i in range(len(a["sec_sizes"])) if i not in dims_a]
+    free_b = [i for i in range(len(b["sec_sizes"])) if i not in dims_b]
+    by = {}
+    for i, blk in b["blocks"].items():
+        by.setdefault(tuple(i[d] for d in dims_b), []).append(
+            (int(np.prod([blk.shape[d] for d in free_b])), int(np.prod([blk.shape[d] for d in dims_b]))))
+    fl = 0
+    for i, blk in a["blocks"].items():
+        m = int(np.prod([blk.shape[d] for d in free_a]))
+        for n, k in by.get(tuple(i[d] for d in dims_a), []):
+            fl += 2 * m * n * k
+    return fl
+
+
+def reference_cpu_time(a, b, dims_a, dims_b, threads, reps, budget_s=30.0):
+    """Times the reference's own btensor::tensordot (oracle/_ref/ref_harness, kind 'reference') or, when the compiled
+    reference is absent, the numpy restatement (kind 'port'). Returns (kind, cores, [ms per rep])."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if os.path.exists(harness):
+        with tempfile.TemporaryDirectory() as td:
+            pa, pb, pc = (os.path.join(td, n) for n in ("A.qtbt", "B.qtbt", "C.qtbt"))
+            dump_qtbt(a, pa)
+            dump_qtbt(b, pb)
+            cmd = [harness, "tdot", pa, pb, ",".join(map(str, dims_a)), ",".join(map(str, dims_b)), pc,
+                   "--reps", str(reps), "--threads", str(threads)]
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=max(600, budget_s * 20), env=env)
+            if out.returncode == 0:
+                ms = [float(l.split()[1]) for l in out.stdout.splitlines() if l.startswith("TIME_MS")]
+                if ms:
+                    return "reference", threads, ms
+            sys.stderr.write("ref_harness failed, falling back to the numpy port: " + out.stderr[-500:] + "\n")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import qtb_oracle as orc  # the one place bench.py executes oracle/ (cpu baseline leg only)
+    oa, ob = orc.BT(**{k: a[k] for k in ("sec_sizes", "cvals", "sel", "blocks")}), orc.BT(
+        **{k: b[k] for k in ("sec_sizes", "cvals", "sel", "blocks")})
+    ms = []
+    for _ in range(max(1, reps)):
+        t0 = time.perf_counter()
+        orc.tensordot(oa, ob, dims_a, dims_b)
+        ms.append((time.perf_counter() - t0) * 1e3)
+    return "port", 1, ms
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from quantit_b200 import workloads as wl
+    cfg = WORKLOADS[args.workload]
+    a, b, da, db = wl.tdot_pair(**cfg)
+    flops = algorithmic_flops(a, b, da, db)
+    threads = os.cpu_count() or 1
+    kind, cores, ms = reference_cpu_time(a, b, da, db, threads, args.steps + args.warmup)
+    ms = ms[args.warmup:] if len(ms) > args.warmup else ms
+    t = float(np.mean(ms))
+    val = flops / (t * 1e-3) / 1e12
+    line = {"impl": "reference", "metric": "block_tensordot_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": len(ms), "warmup": args.warmup, "ms_per_step": t, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, **cfg, "flops_per_step": flops},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(ms)} full {args.workload} contractions (whole workload, no sub-sampling)"},
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def measure_dgemm_peak(torch, n=8192, reps=5):
+    x = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    y = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        z = x @ y
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        z = x @ y
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del x, y, z
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def time_workload(torch, qb, ctx, name, steps, warmup, flush_buf, dist=None):
+    from quantit_b200 import workloads as wl
+    cfg = WORKLOADS[name]
+    a, b, da, db = wl.tdot_pair(**cfg)
+    A, B = qb.BTensor.from_host(**a), qb.BTensor.from_host(**b)
+    info = A.tensordot_info(B, da, db)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    c0 = ctx.counters()
+    for _ in range(warmup):
+        C = A.tensordot(B, da, db)
+        del C
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    c1 = ctx.counters()
+    evs = []
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            flush_buf.zero_()  # L2 flush: 256 MiB write on the same stream, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            C = A.tensordot(B, da, db)  # public API call: plan-cache hit, pool allocation, ONE grouped-GEMM launch
+            e1.record(stream)
+            evs.append((e0, e1))
+            del C
+    ctx.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    c2 = ctx.counters()
+    per = [e0.elapsed_time(e1) for e0, e1 in evs]
+    ms = float(np.mean(per))
+    return {"a": a, "b": b, "da": da, "db": db, "info": info, "ms": ms, "ms_min": float(np.min(per)),
+            "launches": c2["kernel_launches"] - c1["kernel_launches"], "cfg": cfg,
+            "bytes_in": wl.stored_bytes(a) + wl.stored_bytes(b)}
+
+
+def time_e2e(torch, qb, ctx, w, steps, warmup):
+    """C-ABI call with host buffers: pinned inputs -> device, contraction, result -> pinned host buffer."""
+    import ctypes as C
+    from quantit_b200 import engine as eng
+    fa, fb = eng.flatten_host(w["a"]), eng.flatten_host(w["b"])
+    pin = lambda arr: torch.from_numpy(arr).pin_memory()
+    ta, tb = pin(fa["data"]), pin(fb["data"])
+    da, db = np.asarray(w["da"], np.int64), np.asarray(w["db"], np.int64)
+    nob, numel = C.c_int64(), C.c_int64()
+    pi, pf = eng._pi, eng._pf
+    base = [ctx.h, fa["nc"], None,
+            fa["rank"], pi(fa["nsec"]), pi(fa["ss"]), pi(fa["cv"]), pi(fa["sel"]), fa["nb"], pi(fa["idx"]),
+            C.cast(ta.data_ptr(), eng.p_f64),
+            fb["rank"], pi(fb["nsec"]), pi(fb["ss"]), pi(fb["cv"]), pi(fb["sel"]), fb["nb"], pi(fb["idx"]),
+            C.cast(tb.data_ptr(), eng.p_f64),
+            len(da), pi(da), pi(db)]
+    eng._check(ctx.lib.qtb_tensordot_host(*base, C.byref(nob), C.byref(numel), None, None))
+    r_out = fa["rank"] + fb["rank"] - 2 * len(da)
+    cidx = np.zeros(nob.value * r_out, np.int64)
+    tc = torch.empty(numel.value, dtype=torch.float64).pin_memory()
+    call = lambda: eng._check(ctx.lib.qtb_tensordot_host(*base, C.byref(nob), C.byref(numel), pi(cidx),
+                                                          C.cast(tc.data_ptr(), eng.p_f64)))
+    for _ in range(warmup):
+        call()
+    t = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        call()
+        t.append((time.perf_counter() - t0) * 1e3)
+    return float(np.mean(t)), int(ta.numel() + tb.numel()) * 8, int(numel.value) * 8
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="T1", choices=list(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the D=4096 side measurement and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: quantit_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    import quantit_b200 as qb
+    ctx = qb.Context(local)
+    qb.engine._default_ctx = ctx
+    flush_buf = None
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream)):
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    w = time_workload(torch, qb, ctx, args.workload, args.steps, args.warmup, flush_buf, dist)
+    clocks = sampler.stop()
+
+    ms = w["ms"]
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    flops = w["info"]["flops"]
+    value = world * flops / (ms * 1e-3) / 1e12
+
+    e2e_ms, h2d, d2h = time_e2e(torch, qb, ctx, w, max(3, min(args.steps, 10)), 2)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * flops / (e2e_ms * 1e-3) / 1e12
+
+    line = {"metric": "block_tensordot_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, **w["cfg"],
+                       "flops_per_step": flops, "block_gemms": w["info"]["pairs"], "out_blocks": w["info"]["out_blocks"],
+                       "l2": "flushed between steps (256 MiB write outside the per-step CUDA-event pair)",
+                       "parallelism": f"{world} independent contraction(s), one per GPU"},
+            "e2e": {"value": e2e_val, "unit": "TFLOP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": "qtb_tensordot_host (C ABI, pinned host buffers)"},
+            "gpu_launches": w["launches"], "clocks": clocks}
+
+    if rank == 0:
+        peak = measure_dgemm_peak(torch)
+        line["roofline"] = {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                            "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None,
+                            "kernel": "grouped_gemm_kernel (fp64 DMMA.8x8x4)",
+                            "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured live in this run, best of 5; "
+                                           "MEASURED_PEAKS.json has no fp64 entry; nominal B200 fp64 tensor peak 40 TFLOP/s",
+                            }
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            line["roofline"]["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
+        except Exception:
+            pass
+        if not args.no_extra and world == 1:
+            extra = {}
+            for name in ["T2"] if args.workload != "T2" else ["T1"]:
+                sw = time_workload(torch, qb, ctx, name, max(3, min(args.steps, 10)), 3, flush_buf, None)
+                ach = sw["info"]["flops"] / (sw["ms"] * 1e-3) / 1e12
+                extra[name] = {"workload": WORKLOAD_DESC[name], "ms_per_step": sw["ms"], "value": ach, "unit": "TFLOP/s",
+                               "flops_per_step": sw["info"]["flops"], "block_gemms": sw["info"]["pairs"],
+                               "roofline_frac": ach / peak}
+            line["workloads"] = extra
+            threads = os.cpu_count() or 1
+            kind, cores, cms = reference_cpu_time(w["a"], w["b"], w["da"], w["db"], threads, 12)
+            cms = cms[2:] if len(cms) > 4 else cms
+            cval = flops / (float(np.mean(cms)) * 1e-3) / 1e12
+            line["cpu_baseline"] = {"value": cval, "unit": "TFLOP/s", "cores": cores, "kind": kind,
+                                    "ms_per_step": float(np.mean(cms)),
+                                    "sample": f"{len(cms)} full {args.workload} contractions on the host CPU "
+                                              f"({threads} torch threads), same inputs"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -320,29 +320,34 @@ std::unique_ptr<Tensor> make_tensor(Ctx &ctx, const Structure &st_in, i64 nblock
 			QTB_CUDA(cudaMemsetAsync(t->arena->ptr, 0, total * sizeof(double), ctx.stream));
 		else
 		{
-			// source offsets in the GIVEN order
-			std::vector<i64> src_off(nblocks);
-			std::vector<i64> numel_given(nblocks);
+			bool sorted_already = true;
 			for (i64 nb = 0; nb < nblocks; ++nb)
-				numel_given[perm[nb]] = t->block_numel(nb);
-			i64 pos = 0;
-			for (i64 g = 0; g < nblocks; ++g)
-			{
-				src_off[g] = pos;
-				pos += numel_given[g];
+				sorted_already &= (perm[nb] == nb);
+			if (sorted_already)
+			{ // the arena image IS the caller's buffer: one DMA straight from it (direct when the buffer is pinned)
+				QTB_CUDA(cudaMemcpyAsync(t->arena->ptr, host_data, total * sizeof(double), cudaMemcpyHostToDevice,
+				                         ctx.stream));
 			}
-			// stage the packed (aligned) image in pinned memory, one H2D copy
-			double *stage = (double *)ctx.pinned_buf(total * sizeof(double));
-			QTB_CUDA(cudaStreamSynchronize(ctx.stream)); // staging buffer may still be in flight
-			for (i64 nb = 0; nb < nblocks; ++nb)
+			else
 			{
-				const i64 n = t->block_numel(nb);
-				std::memcpy(stage + t->offs[nb], host_data + src_off[perm[nb]], n * sizeof(double));
-				const i64 padded = (n + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
-				if (padded > n)
-					std::memset(stage + t->offs[nb] + n, 0, (padded - n) * sizeof(double));
+				// source offsets in the GIVEN order
+				std::vector<i64> src_off(nblocks);
+				std::vector<i64> numel_given(nblocks);
+				for (i64 nb = 0; nb < nblocks; ++nb)
+					numel_given[perm[nb]] = t->block_numel(nb);
+				i64 pos = 0;
+				for (i64 g = 0; g < nblocks; ++g)
+				{
+					src_off[g] = pos;
+					pos += numel_given[g];
+				}
+				QTB_CUDA(cudaStreamSynchronize(ctx.stream)); // staging buffer may still be in flight
+				double *stage = (double *)ctx.pinned_buf(total * sizeof(double));
+				for (i64 nb = 0; nb < nblocks; ++nb)
+					std::memcpy(stage + t->offs[nb], host_data + src_off[perm[nb]], t->block_numel(nb) * sizeof(double));
+				QTB_CUDA(cudaMemcpyAsync(t->arena->ptr, stage, total * sizeof(double), cudaMemcpyHostToDevice,
+				                         ctx.stream));
 			}
-			QTB_CUDA(cudaMemcpyAsync(t->arena->ptr, stage, total * sizeof(double), cudaMemcpyHostToDevice, ctx.stream));
 			ctx.counters[4] += total * (i64)sizeof(double);
 		}
 	}
@@ -392,25 +397,34 @@ void download(Ctx &ctx, const Tensor &t, double *host_out)
 		tmp = contiguous(ctx, t);
 		src = tmp.get();
 	}
-	// blocks may sit anywhere in the arena (views of larger arenas): copy block by block into a pinned image
 	i64 total = 0;
-	for (i64 b = 0; b < src->nblocks; ++b)
-		total += src->block_numel(b);
-	if (total == 0)
-		return;
-	QTB_CUDA(cudaStreamSynchronize(ctx.stream));
-	double *stage = (double *)ctx.pinned_buf(total * sizeof(double));
-	i64 pos = 0;
+	bool back_to_back = true;
 	for (i64 b = 0; b < src->nblocks; ++b)
 	{
-		const i64 n = src->block_numel(b);
-		if (n)
-			QTB_CUDA(cudaMemcpyAsync(stage + pos, src->arena->ptr + src->offs[b], n * sizeof(double),
-			                         cudaMemcpyDeviceToHost, ctx.stream));
-		pos += n;
+		back_to_back &= (src->offs[b] == src->offs[0] + total);
+		total += src->block_numel(b);
 	}
-	QTB_CUDA(cudaStreamSynchronize(ctx.stream));
-	std::memcpy(host_out, stage, total * sizeof(double));
+	if (total == 0)
+		return;
+	if (back_to_back)
+	{ // one DMA straight into the caller's buffer
+		QTB_CUDA(cudaMemcpyAsync(host_out, src->arena->ptr + src->offs[0], total * sizeof(double),
+		                         cudaMemcpyDeviceToHost, ctx.stream));
+		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+	}
+	else
+	{ // blocks of a view may sit anywhere in a larger arena
+		i64 pos = 0;
+		for (i64 b = 0; b < src->nblocks; ++b)
+		{
+			const i64 n = src->block_numel(b);
+			if (n)
+				QTB_CUDA(cudaMemcpyAsync(host_out + pos, src->arena->ptr + src->offs[b], n * sizeof(double),
+				                         cudaMemcpyDeviceToHost, ctx.stream));
+			pos += n;
+		}
+		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+	}
 	ctx.counters[5] += total * (i64)sizeof(double);
 }
 
@@ -651,6 +665,19 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	{
 		int32_t r = -1, c = -1;
 		int contig = 0;
+		int32_t rs = -1, cs = -1; // affine strides of the two tables, -1 when a table is not affine
+	};
+	auto affine_stride = [](const std::vector<int32_t> &o) -> int32_t
+	{
+		if (o.size() <= 1)
+			return 0;
+		const int64_t s = o[1] - o[0];
+		if (s < 0)
+			return -1;
+		for (size_t i = 0; i < o.size(); ++i)
+			if ((int64_t)o[i] != (int64_t)i * s)
+				return -1;
+		return (int32_t)s;
 	};
 	std::vector<OpTab> atab(a.nblocks), btab(b.nblocks);
 	auto push_pool = [&](const std::vector<int32_t> &v)
@@ -667,6 +694,8 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			auto ro = flat_offsets(a, i, free_a);
 			auto ko = flat_offsets(a, i, dims_a);
 			t.contig = (ko.size() > 1) ? unit_stride(ko) : !(ro.size() > 1 && unit_stride(ro));
+			t.rs = affine_stride(ro);
+			t.cs = affine_stride(ko);
 			t.r = push_pool(ro);
 			t.c = push_pool(ko);
 		}
@@ -680,6 +709,8 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			auto ko = flat_offsets(b, j, dims_b);
 			auto co = flat_offsets(b, j, free_b);
 			t.contig = (co.size() > 1) ? unit_stride(co) : !(ko.size() > 1 && unit_stride(ko));
+			t.rs = affine_stride(ko);
+			t.cs = affine_stride(co);
 			t.r = push_pool(ko);
 			t.c = push_pool(co);
 		}
@@ -732,6 +763,11 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			gp.b_koff = tb.r;
 			gp.b_coff = tb.c;
 			gp.b_ncontig = tb.contig;
+			const bool a_aff = ta.rs >= 0 && ta.cs >= 0, b_aff = tb.rs >= 0 && tb.cs >= 0;
+			gp.a_rs = a_aff ? ta.rs : -1;
+			gp.a_ks = a_aff ? ta.cs : -1;
+			gp.b_ks = b_aff ? tb.rs : -1;
+			gp.b_cs = b_aff ? tb.cs : -1;
 			plan->pairs.push_back(gp);
 			plan->flops += 2 * M * N * Ka;
 		}

@@ -135,14 +135,15 @@ struct Tensor
 	bool block_contiguous(i64 b) const;
 	bool packed_canonical() const; // every block C-contiguous (the layout produced by allocate_packed)
 	void compute_hash();
-	// lay the blocks out back to back (each start aligned to 16 elements = 128 B), C-contiguous; fills strides/offs and
+	// lay the blocks out back to back, C-contiguous; fills strides/offs and
 	// returns the arena size in elements. dims must be set.
 	i64 layout_packed();
 	void dims_from_structure(); // dims[b] = section sizes of index[b]
 	i64 find_block(const i64 *index_) const; // -1 if absent
 };
 
-constexpr i64 kBlockAlign = 16; // elements (128 bytes): every packed block starts on a 128-byte line
+constexpr i64 kBlockAlign = 1; // packed blocks sit back to back: the arena image equals the caller's flat buffer, so
+                                // host<->device transfers are ONE DMA each (cp.async needs only 8-byte alignment)
 
 // sorts blocks lexicographically; returns the permutation applied (new position -> old position)
 std::vector<i64> sort_blocks(i64 rank, std::vector<i64> &index);
@@ -167,6 +168,8 @@ struct GemmPair
 	int32_t b_koff, b_coff;  // k offsets [K], column offsets [N] of the B block
 	int32_t a_kcontig;       // 1: k is the unit-stride direction of A (else rows are)
 	int32_t b_ncontig;       // 1: n is the unit-stride direction of B (else k is)
+	int32_t a_rs, a_ks;      // affine fast path: offset(m,k) = m*a_rs + k*a_ks   (a_rs < 0: use the tables)
+	int32_t b_ks, b_cs;      // affine fast path: offset(k,n) = k*b_ks + n*b_cs   (b_cs < 0: use the tables)
 };
 
 struct Plan

@@ -8,12 +8,18 @@
 //    contracted block index, like the reference's two-pointer merge) and keeps the accumulators in registers across
 //    pairs: no HBM round trip between pairs (the reference's addmm_ reads+writes C once per pair).
 //  * operands are read straight from the (possibly permuted / strided) source blocks: element (m,k) of an operand
-//    matrix lives at base + roff[m] + koff[k]; the two int32 offset tables are built by the planner from the block's
-//    dims/strides, so the permute+reshape the reference materialises is fused into the cp.async operand load.
+//    matrix lives at base + roff(m) + koff(k). roff/koff are affine (m*rs, k*ks) for almost every block of the DMRG
+//    path; otherwise two int32 tables built by the planner. Either way the permute+reshape copy the reference
+//    materialises is fused into the operand load.
 //  * fp64 tensor cores: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — the only fp64 MMA shape sm_100a has; tcgen05 has no
-//    fp64 kind). Operand tiles are staged through a STAGES-deep cp.async pipeline in shared memory, laid out per
-//    operand orientation so that both the async stores and the fragment loads are bank-conflict free.
-//  * persistent CTAs pull tiles (sorted by decreasing cost by the planner) from an atomic counter.
+//    fp64 kind).
+//  * warp-specialised: one producer warpgroup issues the cp.async operand loads into a STAGES-deep shared-memory ring
+//    (completion tracked by mbarriers, cp.async.mbarrier.arrive), the consumer warps only do LDS + DMMA, so the tensor
+//    pipe is not starved by address arithmetic. The producer runs ahead across tile boundaries (it prefetches the next
+//    tile's operands while the consumers finish the current one), which is what keeps the small-block regime
+//    (hundreds of 50x50x50 GEMMs per contraction) from being pipeline-fill bound.
+//  * tiles are assigned statically in a snake order over the planner's cost-sorted list; ragged block edges are
+//    skipped at 8-row/8-column MMA granularity.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -23,17 +29,37 @@
 namespace qtb
 {
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid)
+// ---- PTX helpers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async8(unsigned smem, const void *gmem, bool valid)
 {
-	unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
 	int sz = valid ? 8 : 0; // src-size 0 -> the 8 destination bytes are zero-filled
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem), "l"(gmem), "r"(sz));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
-	asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar)
+{ // the arrival fires when every cp.async issued so far by this thread has landed
+	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred P1;\n"
+	             "LAB_WAIT:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	             "@P1 bra DONE;\n"
+	             "bra LAB_WAIT;\n"
+	             "DONE:\n"
+	             "}\n" ::"r"(bar),
+	             "r"(parity)
+	             : "memory");
 }
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -42,253 +68,315 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 	             : "d"(a), "d"(b));
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_, int MINB_, bool REALLOC_>
 struct GemmCfg
 {
+	static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+	static constexpr bool REALLOC = REALLOC_;
 	static constexpr int kWarpsM = BM / WM;
 	static constexpr int kWarpsN = BN / WN;
-	static constexpr int kThreads = kWarpsM * kWarpsN * 32;
+	static constexpr int kConsWarps = kWarpsM * kWarpsN;
+	static constexpr int kProdThreads = 128; // one warpgroup
+	static constexpr int kThreads = kProdThreads + kConsWarps * 32;
 	static constexpr int kPad = 4;
 	// an operand tile is stored either "k-major" [rows][BK+4] or "row-major" [BK][rows+4]; reserve the larger
 	static constexpr int kASize = (BM * (BK + kPad) > BK * (BM + kPad)) ? BM * (BK + kPad) : BK * (BM + kPad);
 	static constexpr int kBSize = (BN * (BK + kPad) > BK * (BN + kPad)) ? BN * (BK + kPad) : BK * (BN + kPad);
 	static constexpr int kStage = kASize + kBSize;
-	static constexpr size_t kSmemBytes = size_t(STAGES) * kStage * sizeof(double);
-	static constexpr int kAPerThread = BM * BK / kThreads;
-	static constexpr int kBPerThread = BN * BK / kThreads;
-	static_assert(BM * BK % kThreads == 0 && BN * BK % kThreads == 0, "tile/threads mismatch");
+	static constexpr size_t kSmemBytes = size_t(STAGES) * kStage * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+	static constexpr int kAPerThread = BM * BK / kProdThreads;
+	static constexpr int kBPerThread = BN * BK / kProdThreads;
+	static_assert(BM * BK % kProdThreads == 0 && BN * BK % kProdThreads == 0, "tile/threads mismatch");
 	static_assert(BM % 16 == 0 && BN % 16 == 0 && BK % 4 == 0, "tile shape");
+	static_assert(kConsWarps % 4 == 0, "consumer warps must form whole warpgroups");
 };
 
-// iterator over the (pair, k-chunk) steps of one output block
-struct StepIter
-{
-	int pair;  // current pair index (absolute)
-	int chunk; // k-chunk inside the pair
-	int nchunk;
-};
 
-template <class Cfg, int BM, int BN, int BK, int WM, int WN, int STAGES>
-__global__ void __launch_bounds__(Cfg::kThreads)
-    grouped_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles, const GemmOut *__restrict__ outs,
-                        const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
-                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
-                        int *__restrict__ counter)
+// Producer side: one operand tile [R rows x BK] of a block matrix into shared memory.
+//   kcontig : consecutive threads walk k  -> smem layout [R][BK+4]   (k-major)
+//   else    : consecutive threads walk r  -> smem layout [BK][R+4]   (row-major)
+// element (r,k) lives at base + roff(r) + koff(k); affine: r*rs + k*ks, else the planner's int32 tables.
+template <class Cfg, int R, bool IS_A>
+__device__ __forceinline__ void load_operand(int kcontig, bool affine, unsigned smem_dst, const double *__restrict__ base,
+                                             const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
+                                             int ks, int r0, int Rmax, int k0, int K, int pt)
 {
-	extern __shared__ __align__(16) double smem[];
-	__shared__ int s_tile;
-	const int tid = threadIdx.x;
-	const int lane = tid & 31;
-	const int warp = tid >> 5;
-	const int wm0 = (warp / Cfg::kWarpsN) * WM;
-	const int wn0 = (warp % Cfg::kWarpsN) * WN;
-	const int g = lane >> 2; // fragment row (A) / column (B) inside an 8x8x4 MMA
-	const int q = lane & 3;  // fragment k index
-	constexpr int MI = WM / 8;
-	constexpr int NI = WN / 8;
-
-	for (;;)
+	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads;
+	constexpr int PER = R * BK / NT;
+	if (kcontig)
 	{
-		if (tid == 0)
-			s_tile = atomicAdd(counter, 1);
-		__syncthreads();
-		const int t = s_tile;
-		__syncthreads();
-		if (t >= ntiles)
-			break;
-		const GemmTile tile = tiles[t];
-		const GemmOut ob = outs[tile.out_blk];
-		const int M = ob.M, N = ob.N;
-		const int m0 = tile.m0, n0 = tile.n0;
-
-		double acc[MI][NI][2];
+		const int k = pt % BK, rbase = pt / BK;
+		const bool kok = (k0 + k) < K;
+		const int koff = kok ? (affine ? (k0 + k) * ks : ktab[k0 + k]) : 0;
+		unsigned dst = smem_dst + (rbase * (BK + PAD) + k) * 8;
 #pragma unroll
-		for (int i = 0; i < MI; ++i)
-#pragma unroll
-			for (int j = 0; j < NI; ++j)
-				acc[i][j][0] = acc[i][j][1] = 0.0;
-
-		// total number of (pair, chunk) steps of this block
-		int total_steps = 0;
-		for (int p = ob.pair_begin; p < ob.pair_end; ++p)
-			total_steps += (pairs[p].K + BK - 1) / BK;
-
-		// producer iterator
-		int p_pair = ob.pair_begin, p_chunk = 0;
-		int p_nchunk = (pairs[p_pair].K + BK - 1) / BK;
-		// consumer iterator
-		int c_pair = ob.pair_begin, c_chunk = 0;
-		int c_nchunk = p_nchunk;
-
-		auto issue_load = [&](int stage)
+		for (int i = 0; i < PER; ++i)
 		{
-			const GemmPair pr = pairs[p_pair];
-			double *As = smem + stage * Cfg::kStage;
-			double *Bs = As + Cfg::kASize;
-			const int k0 = p_chunk * BK;
-			const double *Ab = A + pr.a_off;
-			const double *Bb = B + pr.b_off;
-			const int32_t *aro = offpool + pr.a_roff;
-			const int32_t *ako = offpool + pr.a_koff;
-			const int32_t *bko = offpool + pr.b_koff;
-			const int32_t *bco = offpool + pr.b_coff;
-			if (pr.a_kcontig)
-			{ // consecutive threads walk k: smem layout [BM][BK+4]
-#pragma unroll
-				for (int i = 0; i < Cfg::kAPerThread; ++i)
-				{
-					const int e = tid + i * Cfg::kThreads;
-					const int m = e / BK, k = e % BK;
-					const bool ok = (m0 + m < M) && (k0 + k < pr.K);
-					const double *src = ok ? Ab + aro[m0 + m] + ako[k0 + k] : Ab;
-					cp_async8(As + m * (BK + Cfg::kPad) + k, src, ok);
-				}
-			}
-			else
-			{ // consecutive threads walk m: smem layout [BK][BM+4]
-#pragma unroll
-				for (int i = 0; i < Cfg::kAPerThread; ++i)
-				{
-					const int e = tid + i * Cfg::kThreads;
-					const int k = e / BM, m = e % BM;
-					const bool ok = (m0 + m < M) && (k0 + k < pr.K);
-					const double *src = ok ? Ab + aro[m0 + m] + ako[k0 + k] : Ab;
-					cp_async8(As + k * (BM + Cfg::kPad) + m, src, ok);
-				}
-			}
-			if (pr.b_ncontig)
-			{ // consecutive threads walk n: smem layout [BK][BN+4]
-#pragma unroll
-				for (int i = 0; i < Cfg::kBPerThread; ++i)
-				{
-					const int e = tid + i * Cfg::kThreads;
-					const int k = e / BN, n = e % BN;
-					const bool ok = (n0 + n < N) && (k0 + k < pr.K);
-					const double *src = ok ? Bb + bko[k0 + k] + bco[n0 + n] : Bb;
-					cp_async8(Bs + k * (BN + Cfg::kPad) + n, src, ok);
-				}
-			}
-			else
-			{ // consecutive threads walk k: smem layout [BN][BK+4]
-#pragma unroll
-				for (int i = 0; i < Cfg::kBPerThread; ++i)
-				{
-					const int e = tid + i * Cfg::kThreads;
-					const int n = e / BK, k = e % BK;
-					const bool ok = (n0 + n < N) && (k0 + k < pr.K);
-					const double *src = ok ? Bb + bko[k0 + k] + bco[n0 + n] : Bb;
-					cp_async8(Bs + n * (BK + Cfg::kPad) + k, src, ok);
-				}
-			}
-			if (++p_chunk == p_nchunk)
-			{
-				p_chunk = 0;
-				++p_pair;
-				if (p_pair < ob.pair_end)
-					p_nchunk = (pairs[p_pair].K + BK - 1) / BK;
-			}
-		};
-
-		// prologue: fill STAGES-1 stages
-		int issued = 0;
-#pragma unroll
-		for (int s = 0; s < STAGES - 1; ++s)
-		{
-			if (issued < total_steps)
-			{
-				issue_load(s);
-				++issued;
-			}
-			cp_async_commit();
+			const int r = r0 + rbase + i * (NT / BK);
+			const bool ok = kok && (r < Rmax);
+			const int off = ok ? (affine ? r * rs : rtab[r]) + koff : 0;
+			cp_async8(dst, base + off, ok);
+			dst += (NT / BK) * (BK + PAD) * 8;
 		}
-
-		for (int step = 0; step < total_steps; ++step)
+	}
+	else
+	{
+		const int r = pt % R, kbase = pt / R;
+		const bool rok = (r0 + r) < Rmax;
+		const int roff = rok ? (affine ? (r0 + r) * rs : rtab[r0 + r]) : 0;
+		unsigned dst = smem_dst + (kbase * (R + PAD) + r) * 8;
+#pragma unroll
+		for (int i = 0; i < PER; ++i)
 		{
-			cp_async_wait<STAGES - 2>();
-			__syncthreads();
-			// refill the stage that was consumed in the previous iteration
-			if (issued < total_steps)
-			{
-				issue_load((step + STAGES - 1) % STAGES);
-				++issued;
-			}
-			cp_async_commit();
-
-			const int stage = step % STAGES;
-			const double *As = smem + stage * Cfg::kStage;
-			const double *Bs = As + Cfg::kASize;
-			const GemmPair pr = pairs[c_pair];
-			const int sa_m = pr.a_kcontig ? (BK + Cfg::kPad) : 1;
-			const int sa_k = pr.a_kcontig ? 1 : (BM + Cfg::kPad);
-			const int sb_k = pr.b_ncontig ? (BN + Cfg::kPad) : 1;
-			const int sb_n = pr.b_ncontig ? 1 : (BK + Cfg::kPad);
-#pragma unroll
-			for (int kk = 0; kk < BK; kk += 4)
-			{
-				double af[MI], bf[NI];
-#pragma unroll
-				for (int i = 0; i < MI; ++i)
-					af[i] = As[(wm0 + i * 8 + g) * sa_m + (kk + q) * sa_k];
-#pragma unroll
-				for (int j = 0; j < NI; ++j)
-					bf[j] = Bs[(kk + q) * sb_k + (wn0 + j * 8 + g) * sb_n];
-#pragma unroll
-				for (int i = 0; i < MI; ++i)
-#pragma unroll
-					for (int j = 0; j < NI; ++j)
-						dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-			}
-			if (++c_chunk == c_nchunk)
-			{
-				c_chunk = 0;
-				++c_pair;
-				if (c_pair < ob.pair_end)
-					c_nchunk = (pairs[c_pair].K + BK - 1) / BK;
-			}
+			const int k = k0 + kbase + i * (NT / R);
+			const bool ok = rok && (k < K);
+			const int off = ok ? (affine ? k * ks : ktab[k]) + roff : 0;
+			cp_async8(dst, base + off, ok);
+			dst += (NT / R) * (R + PAD) * 8;
 		}
-		cp_async_wait<0>();
-
-		// epilogue: the output block is a fresh packed row-major [M,N] matrix
-		double *Cb = C + ob.c_off;
-#pragma unroll
-		for (int i = 0; i < MI; ++i)
-		{
-			const int m = m0 + wm0 + i * 8 + g;
-			if (m < M)
-			{
-#pragma unroll
-				for (int j = 0; j < NI; ++j)
-				{
-					const int n = n0 + wn0 + j * 8 + 2 * q;
-					double *dst = Cb + (size_t)m * N + n;
-					if (n + 1 < N)
-					{
-						if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)
-							*reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
-						else
-						{
-							dst[0] = acc[i][j][0];
-							dst[1] = acc[i][j][1];
-						}
-					}
-					else if (n < N)
-						dst[0] = acc[i][j][0];
-				}
-			}
-		}
-		__syncthreads(); // all warps done with the stages before the next tile's prologue overwrites them
 	}
 }
 
-using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 3>;
-using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 3>;
+// snake order over the cost-sorted tile list: round r visits the CTAs forwards (even r) or backwards (odd r)
+__device__ __forceinline__ int tile_of(int round, int cta, int ncta)
+{
+	return round * ncta + ((round & 1) ? (ncta - 1 - cta) : cta);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
+    grouped_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles, const GemmOut *__restrict__ outs,
+                        const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
+                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C)
+{
+	constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
+	constexpr int PAD = Cfg::kPad;
+	extern __shared__ __align__(16) double smem[];
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::kStage);
+	const unsigned full0 = smem_u32(bars);           // full[s]  : producer -> consumers
+	const unsigned empty0 = smem_u32(bars + STAGES); // empty[s] : consumers -> producer
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5;
+	const int lane = tid & 31;
+
+	if (tid == 0)
+	{
+		for (int s = 0; s < STAGES; ++s)
+		{
+			mbar_init(full0 + 8 * s, Cfg::kProdThreads);
+			mbar_init(empty0 + 8 * s, Cfg::kConsWarps);
+		}
+	}
+	__syncthreads();
+
+	const int ncta = gridDim.x, cta = blockIdx.x;
+
+	if (warp < 4)
+	{
+		// ================================================ PRODUCER ================================================
+		if constexpr (Cfg::REALLOC)
+			asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+		const int pt = tid; // 0..127
+		int stage = 0;
+		unsigned phase = 0;
+		for (int round = 0;; ++round)
+		{
+			const int t = tile_of(round, cta, ncta);
+			if (round * ncta >= ntiles)
+				break;
+			if (t >= ntiles)
+				continue;
+			const GemmTile tile = tiles[t];
+			const GemmOut ob = outs[tile.out_blk];
+			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
+			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+			{
+				const GemmPair pr = pairs[p];
+				const double *Ab = A + pr.a_off;
+				const double *Bb = B + pr.b_off;
+				const int32_t *aro = offpool + pr.a_roff;
+				const int32_t *ako = offpool + pr.a_koff;
+				const int32_t *bko = offpool + pr.b_koff;
+				const int32_t *bco = offpool + pr.b_coff;
+				const bool a_aff = pr.a_rs >= 0, b_aff = pr.b_cs >= 0;
+				const int nchunk = (pr.K + BK - 1) / BK;
+				for (int ch = 0; ch < nchunk; ++ch)
+				{
+					mbar_wait(empty0 + 8 * stage, phase ^ 1);
+					const unsigned As = smem_u32(smem + stage * Cfg::kStage);
+					const unsigned Bs = As + Cfg::kASize * 8;
+					const int k0 = ch * BK;
+					load_operand<Cfg, BM, true>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt);
+					load_operand<Cfg, BN, false>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt);
+					mbar_arrive_cp_async(full0 + 8 * stage);
+					if (++stage == STAGES)
+					{
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+			}
+		}
+		// drain: the async arrivals must have fired before the CTA (and its shared memory) goes away
+		asm volatile("cp.async.wait_all;\n" ::: "memory");
+	}
+	else
+	{
+		// ================================================ CONSUMERS ===============================================
+		if constexpr (Cfg::REALLOC)
+			asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+		const int cw = warp - 4;
+		const int wm0 = (cw / Cfg::kWarpsN) * WM;
+		const int wn0 = (cw % Cfg::kWarpsN) * WN;
+		const int g = lane >> 2; // fragment row (A) / column (B) inside an 8x8x4 MMA
+		const int q = lane & 3;  // fragment k index
+		constexpr int MI = WM / 8;
+		constexpr int NI = WN / 8;
+		int stage = 0;
+		unsigned phase = 0;
+		for (int round = 0;; ++round)
+		{
+			const int t = tile_of(round, cta, ncta);
+			if (round * ncta >= ntiles)
+				break;
+			if (t >= ntiles)
+				continue;
+			const GemmTile tile = tiles[t];
+			const GemmOut ob = outs[tile.out_blk];
+			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
+			// number of 8-row / 8-column MMA groups of this warp that intersect the block
+			int mi_valid = (M - m0 - wm0 + 7) / 8;
+			mi_valid = mi_valid < 0 ? 0 : (mi_valid > MI ? MI : mi_valid);
+			int nj_valid = (N - n0 - wn0 + 7) / 8;
+			nj_valid = nj_valid < 0 ? 0 : (nj_valid > NI ? NI : nj_valid);
+			const bool full_tile = (mi_valid == MI) && (nj_valid == NI);
+			const bool any = (mi_valid > 0) && (nj_valid > 0);
+
+			double acc[MI][NI][2];
+#pragma unroll
+			for (int i = 0; i < MI; ++i)
+#pragma unroll
+				for (int j = 0; j < NI; ++j)
+					acc[i][j][0] = acc[i][j][1] = 0.0;
+
+			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+			{
+				const int K = pairs[p].K;
+				const int a_kc = pairs[p].a_kcontig, b_nc = pairs[p].b_ncontig;
+				const int sa_m = a_kc ? (BK + PAD) : 1;
+				const int sa_k = a_kc ? 1 : (BM + PAD);
+				const int sb_k = b_nc ? (BN + PAD) : 1;
+				const int sb_n = b_nc ? 1 : (BK + PAD);
+				const int nchunk = (K + BK - 1) / BK;
+				for (int ch = 0; ch < nchunk; ++ch)
+				{
+					mbar_wait(full0 + 8 * stage, phase);
+					const double *As = smem + stage * Cfg::kStage;
+					const double *Bs = As + Cfg::kASize;
+					const double *Ap = As + (wm0 + g) * sa_m + q * sa_k;
+					const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n;
+					if (full_tile)
+					{
+#pragma unroll
+						for (int kk = 0; kk < BK; kk += 4)
+						{
+							double af[MI], bf[NI];
+#pragma unroll
+							for (int i = 0; i < MI; ++i)
+								af[i] = Ap[i * 8 * sa_m + kk * sa_k];
+#pragma unroll
+							for (int j = 0; j < NI; ++j)
+								bf[j] = Bp[kk * sb_k + j * 8 * sb_n];
+#pragma unroll
+							for (int i = 0; i < MI; ++i)
+#pragma unroll
+								for (int j = 0; j < NI; ++j)
+									dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+						}
+					}
+					else if (any)
+					{
+						const int kmax = (K - ch * BK) < BK ? (K - ch * BK) : BK;
+#pragma unroll
+						for (int kk = 0; kk < BK; kk += 4)
+						{
+							if (kk < kmax)
+							{
+								double af[MI], bf[NI];
+#pragma unroll
+								for (int i = 0; i < MI; ++i)
+									af[i] = (i < mi_valid) ? Ap[i * 8 * sa_m + kk * sa_k] : 0.0;
+#pragma unroll
+								for (int j = 0; j < NI; ++j)
+									bf[j] = (j < nj_valid) ? Bp[kk * sb_k + j * 8 * sb_n] : 0.0;
+#pragma unroll
+								for (int i = 0; i < MI; ++i)
+									if (i < mi_valid)
+									{
+#pragma unroll
+										for (int j = 0; j < NI; ++j)
+											if (j < nj_valid)
+												dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+									}
+							}
+						}
+					}
+					__syncwarp();
+					if (lane == 0)
+						mbar_arrive(empty0 + 8 * stage);
+					if (++stage == STAGES)
+					{
+						stage = 0;
+						phase ^= 1;
+					}
+				}
+			}
+
+			// epilogue: the output block is a fresh packed row-major [M,N] matrix
+			if (any)
+			{
+				double *Cb = C + ob.c_off;
+#pragma unroll
+				for (int i = 0; i < MI; ++i)
+				{
+					const int m = m0 + wm0 + i * 8 + g;
+					if (m < M)
+					{
+#pragma unroll
+						for (int j = 0; j < NI; ++j)
+						{
+							const int n = n0 + wn0 + j * 8 + 2 * q;
+							double *dst = Cb + (size_t)m * N + n;
+							if (n + 1 < N)
+							{
+								if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+									*reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+								else
+								{
+									dst[0] = acc[i][j][0];
+									dst[1] = acc[i][j][1];
+								}
+							}
+							else if (n < N)
+								dst[0] = acc[i][j][0];
+						}
+					}
+				}
+			}
+		}
+	}
+}
+
+//                     BM   BN  BK  WM  WN  ST MINB realloc
+using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 4, 2, false>;   // 4 consumer warps + producer warpgroup = 256 threads
+using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + producer warpgroup = 384 threads
 
 static int g_blocks_per_sm[2] = {0, 0};
 
-template <class Cfg, int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <class Cfg>
 static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c)
 {
-	auto kern = grouped_gemm_kernel<Cfg, BM, BN, BK, WM, WN, STAGES>;
+	auto kern = grouped_gemm_kernel<Cfg>;
 	if (g_blocks_per_sm[which] == 0)
 	{
 		QTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
@@ -300,9 +388,8 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 	int grid = ctx.sm_count * g_blocks_per_sm[which];
 	if (grid > ntiles)
 		grid = ntiles;
-	QTB_CUDA(cudaMemsetAsync(plan.d_counter, 0, sizeof(int), ctx.stream));
 	kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(plan.d_tiles, ntiles, plan.d_outs, plan.d_pairs,
-	                                                            plan.d_offpool, a, b, c, plan.d_counter);
+	                                                            plan.d_offpool, a, b, c);
 	QTB_CUDA(cudaGetLastError());
 }
 
@@ -311,9 +398,9 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 	if (plan.tiles.empty())
 		return;
 	if (plan.tile_cfg == 0)
-		launch_cfg<Cfg64, 64, 64, 16, 32, 32, 3>(ctx, 0, plan, a, b, c);
+		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c);
 	else
-		launch_cfg<Cfg128, 128, 128, 16, 64, 32, 3>(ctx, 1, plan, a, b, c);
+		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c);
 	ctx.counters[0] += 1;
 	ctx.counters[1] += 1;
 	ctx.counters[6] += plan.flops;

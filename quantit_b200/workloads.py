@@ -127,13 +127,15 @@ def random_btensor(rng: np.random.Generator, rank: int, max_sec: int = 4, max_si
             sizes = [int(x) for x in rng.integers(1, max_size + 1, ns)]
             charges = [tuple(int(x) for x in rng.integers(-2, 3, nc)) for _ in range(ns)]
             legs.append((sizes, charges))
-    if sel is None:
-        sel = tuple(int(x) for x in rng.integers(-1, 2, nc))
+    if sel is None:  # the flux of a random block, so that at least one block is allowed
+        pick = [int(rng.integers(0, len(l[0]))) for l in legs]
+        sel = tuple(sum(legs[d][1][i][c] for d, i in enumerate(pick)) for c in range(nc))
     sh = shape(legs, sel)
     out = dict(sh)
     out["blocks"] = {}
-    for idx in allowed_indices(sh):
-        if rng.random() < fill:
+    allowed = allowed_indices(sh)
+    for n, idx in enumerate(allowed):
+        if rng.random() < fill or (n == len(allowed) - 1 and not out["blocks"]):
             dims = tuple(sh["sec_sizes"][d][i] for d, i in enumerate(idx))
             out["blocks"][idx] = rng.standard_normal(dims)
     return out
