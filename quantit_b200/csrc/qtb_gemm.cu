@@ -93,47 +93,96 @@ struct GemmCfg
 
 
 // Producer side: one operand tile [R rows x BK] of a block matrix into shared memory.
-//   kcontig : consecutive threads walk k  -> smem layout [R][BK+4]   (k-major)
-//   else    : consecutive threads walk r  -> smem layout [BK][R+4]   (row-major)
-// element (r,k) lives at base + roff(r) + koff(k); affine: r*rs + k*ks, else the planner's int32 tables.
-template <class Cfg, int R, bool IS_A>
-__device__ __forceinline__ void load_operand(int kcontig, bool affine, unsigned smem_dst, const double *__restrict__ base,
-                                             const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
-                                             int ks, int r0, int Rmax, int k0, int K, int pt)
+//   KC (k-contiguous source): consecutive threads walk k  -> smem layout [R][BK+4]   (k-major)
+//   else                    : consecutive threads walk r  -> smem layout [BK][R+4]   (row-major)
+// element (r,k) lives at base + roff(r) + koff(k); AFF: r*rs + k*ks, else the planner's int32 tables.
+// FULL: the tile lies entirely inside the block (no bounds checks, no zero fill) — the hot path: one address
+// computation + one LDGSTS per element.
+__device__ __forceinline__ void cp_async8_full(unsigned smem, const void *gmem)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem), "l"(gmem));
+}
+
+template <class Cfg, int R, bool AFF, bool KC, bool FULL>
+__device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__restrict__ base,
+                                          const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
+                                          int ks, int r0, int Rmax, int k0, int K, int pt)
 {
 	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads;
 	constexpr int PER = R * BK / NT;
-	if (kcontig)
+	if constexpr (KC)
 	{
 		const int k = pt % BK, rbase = pt / BK;
-		const bool kok = (k0 + k) < K;
-		const int koff = kok ? (affine ? (k0 + k) * ks : ktab[k0 + k]) : 0;
-		unsigned dst = smem_dst + (rbase * (BK + PAD) + k) * 8;
+		const int kg = k0 + k;
+		const bool kok = FULL || (kg < K);
+		const int kc = FULL ? kg : (kok ? kg : 0);
+		const double *src_k = base + (AFF ? (int64_t)kc * ks : (int64_t)ktab[kc]);
+		const unsigned dst = smem_dst + (rbase * (BK + PAD) + k) * 8;
 #pragma unroll
 		for (int i = 0; i < PER; ++i)
 		{
-			const int r = r0 + rbase + i * (NT / BK);
-			const bool ok = kok && (r < Rmax);
-			const int off = ok ? (affine ? r * rs : rtab[r]) + koff : 0;
-			cp_async8(dst, base + off, ok);
-			dst += (NT / BK) * (BK + PAD) * 8;
+			int r = r0 + rbase + i * (NT / BK);
+			if constexpr (!FULL)
+				r = r < Rmax ? r : Rmax - 1; // rows past the block edge re-read the last row: results are never stored
+			const double *src = src_k + (AFF ? (int64_t)r * rs : (int64_t)rtab[r]);
+			if constexpr (FULL)
+				cp_async8_full(dst + i * ((NT / BK) * (BK + PAD) * 8), src);
+			else
+				cp_async8(dst + i * ((NT / BK) * (BK + PAD) * 8), src, kok); // k tail is zero-filled
 		}
 	}
 	else
 	{
 		const int r = pt % R, kbase = pt / R;
-		const bool rok = (r0 + r) < Rmax;
-		const int roff = rok ? (affine ? (r0 + r) * rs : rtab[r0 + r]) : 0;
-		unsigned dst = smem_dst + (kbase * (R + PAD) + r) * 8;
+		int rg = r0 + r;
+		if constexpr (!FULL)
+			rg = rg < Rmax ? rg : Rmax - 1;
+		const double *src_r = base + (AFF ? (int64_t)rg * rs : (int64_t)rtab[rg]);
+		const unsigned dst = smem_dst + (kbase * (R + PAD) + r) * 8;
 #pragma unroll
 		for (int i = 0; i < PER; ++i)
 		{
-			const int k = k0 + kbase + i * (NT / R);
-			const bool ok = rok && (k < K);
-			const int off = ok ? (affine ? k * ks : ktab[k]) + roff : 0;
-			cp_async8(dst, base + off, ok);
-			dst += (NT / R) * (R + PAD) * 8;
+			const int kg = k0 + kbase + i * (NT / R);
+			const bool kok = FULL || (kg < K);
+			const int kc = FULL ? kg : (kok ? kg : 0);
+			const double *src = src_r + (AFF ? (int64_t)kc * ks : (int64_t)ktab[kc]);
+			if constexpr (FULL)
+				cp_async8_full(dst + i * ((NT / R) * (R + PAD) * 8), src);
+			else
+				cp_async8(dst + i * ((NT / R) * (R + PAD) * 8), src, kok);
 		}
+	}
+}
+
+template <class Cfg, int R>
+__device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned smem_dst, const double *__restrict__ base,
+                                             const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
+                                             int ks, int r0, int Rmax, int k0, int K, int pt)
+{
+	const bool full = (r0 + R <= Rmax) && (k0 + Cfg::BK <= K);
+	if (affine)
+	{
+		if (kcontig)
+		{
+			if (full)
+				load_tile<Cfg, R, true, true, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+			else
+				load_tile<Cfg, R, true, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+		}
+		else
+		{
+			if (full)
+				load_tile<Cfg, R, true, false, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+			else
+				load_tile<Cfg, R, true, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+		}
+	}
+	else
+	{ // table-driven gather (blocks whose merged free / contracted dims are not a single stride): always bounds-safe
+		if (kcontig)
+			load_tile<Cfg, R, false, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+		else
+			load_tile<Cfg, R, false, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
 	}
 }
 
@@ -175,7 +224,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 	{
 		// ================================================ PRODUCER ================================================
 		if constexpr (Cfg::REALLOC)
-			asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+			asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
 		const int pt = tid; // 0..127
 		int stage = 0;
 		unsigned phase = 0;
@@ -206,8 +255,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					const unsigned As = smem_u32(smem + stage * Cfg::kStage);
 					const unsigned Bs = As + Cfg::kASize * 8;
 					const int k0 = ch * BK;
-					load_operand<Cfg, BM, true>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt);
-					load_operand<Cfg, BN, false>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt);
+					load_operand<Cfg, BM>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt);
+					load_operand<Cfg, BN>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt);
 					mbar_arrive_cp_async(full0 + 8 * stage);
 					if (++stage == STAGES)
 					{
@@ -224,7 +273,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 	{
 		// ================================================ CONSUMERS ===============================================
 		if constexpr (Cfg::REALLOC)
-			asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+			asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n");
 		const int cw = warp - 4;
 		const int wm0 = (cw / Cfg::kWarpsN) * WM;
 		const int wn0 = (cw % Cfg::kWarpsN) * WN;
