@@ -1,0 +1,34 @@
+"""CPU tests of the host-side logic: workload generators and the QTBT exchange format."""
+import numpy as np
+
+import qtb_oracle as orc
+from quantit_b200 import workloads as wl
+
+
+def test_bond_generator():
+    for n, D, s in [(41, 2048, 6.0), (15, 4096, 1.6), (17, 8192, 1.8), (5, 24, 1.0)]:
+        sizes, charges = wl.bond(n, D, s, 2)
+        assert sum(sizes) == D and len(sizes) == n and min(sizes) >= 1
+        assert charges[n // 2] == (0,) and charges[0] == (-2 * (n // 2),)
+
+
+def test_heisenberg_W_is_the_reference_mpo():
+    """dense W equals the reference's Heisenberg_impl tensor (sources/models.cpp:24-57) for J' = 1/4"""
+    W = orc.BT(**wl.heisenberg_W())
+    dense = W.to_dense()
+    sz, sp = np.diag([1.0, -1.0]), np.array([[0.0, 1.0], [0.0, 0.0]])
+    assert np.allclose(dense[4, :, 3, :], 0.25 * sz) and np.allclose(dense[3, :, 0, :], sz)
+    assert np.allclose(dense[1, :, 0, :], sp) and np.allclose(dense[4, :, 1, :], 0.5 * sp.T)
+    # two-site Hamiltonian from the MPO: <s1' s2'| H |s1 s2> = J'(2 S+S- + 2 S-S+ + SzSz)
+    H2 = orc.compute_2sites_hamil(W, W).to_dense()[4, :, :, 0, :, :].reshape(4, 4)
+    want = 0.25 * (np.kron(sz, sz) + 2 * np.kron(sp, sp.T) + 2 * np.kron(sp.T, sp))
+    assert np.allclose(H2, want)
+
+
+def test_qtbt_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    t = orc.BT(**wl.random_btensor(rng, 3, nc=2))
+    p = str(tmp_path / "t.qtbt")
+    orc.write_qtbt(t, p)
+    r = orc.read_qtbt(p)
+    assert orc.same_structure(t, r) and orc.max_rel_err(t, r) == 0.0
