@@ -122,6 +122,11 @@ qtb_status qtb_tensordot_host(qtb_ctx *ctx, int64_t nc, const int64_t *mods,
 /* out = alpha*a + beta*b with the union of the two block lists (btensor::add, btensor.cpp:2666-2752) */
 qtb_status qtb_axpby(qtb_ctx *ctx, double alpha, const qtb_tensor *a, double beta, const qtb_tensor *b,
                      qtb_tensor **out);
+/* btensor::add(other, alpha) = a + alpha*b exactly as the reference computes it (btensor.cpp:2666-2752): its
+ * flat_map::merge (flat_map.h:350-425) also multiplies by alpha the blocks of `a` that sort before every block of `b`;
+ * that observed behaviour is reproduced (it is visible in `psi_ip -= state*a0`, dmrg.cpp:595). qtb_axpby is the plain
+ * linear combination. */
+qtb_status qtb_add(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double alpha, qtb_tensor **out);
 /* <a,b> = tensordot over every index (dmrg.cpp:593): result written to *host_out (one device->host sync) */
 qtb_status qtb_dot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double *host_out);
 /* a *= s in place */
@@ -149,6 +154,26 @@ qtb_status qtb_env_right(qtb_ctx *ctx, const qtb_tensor *h, const qtb_tensor *mp
 /* two_sites_update = one_step_lanczos + eig2x2Mat + recombination, dmrg.cpp:543-651. */
 qtb_status qtb_two_sites_update(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
                                 const qtb_tensor *renv, double *energy, qtb_tensor **psi_out);
+
+/* ---- two-site DMRG driver (replaces quantit::dmrg(bMPO&, bMPS&, const dmrg_options&, dmrg_logger&), dmrg.h:39,
+ *      dmrg.cpp:92-100 -> details::dmrg_impl :219-273, generate_env :370-409, compute_2sitesHamil :503-515, sweep :127-142,
+ *      dmrg_2sites_update::operator() :163-206). Field names follow include/dmrg_options.h:15-34. ------------------- */
+typedef struct qtb_dmrg_options
+{
+	double cutoff;                /* 1e-6   */
+	double convergence_criterion; /* 1e-5   */
+	int64_t maximum_bond;         /* < 0: unlimited (SIZE_MAX in the reference) */
+	int64_t minimum_bond;         /* 4      */
+	int64_t maximum_iterations;   /* 1000   */
+} qtb_dmrg_options;
+/* `mps` is in/out: the handles of the sites that were updated are freed and replaced. `oc` is the orthogonality
+ * centre (in/out). `sweep_energy` / `sweep_seconds` / `sweep_mid_bond` (each [maximum_iterations], may be NULL) receive
+ * what the reference's dmrg_log_sweeptime logger records (dmrg_logger.h:133-185). The state, its environments and
+ * the Krylov vectors never leave the GPU; per two-site update the host reads back one 64-byte scalar record and the
+ * singular values. */
+qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_tensor **mps, int64_t *oc,
+                    const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, double *sweep_energy,
+                    double *sweep_seconds, int64_t *sweep_mid_bond);
 
 #ifdef __cplusplus
 }

@@ -332,18 +332,92 @@ def mul_bcast(big: BT, small: BT) -> BT:
     return out
 
 
+def flat_map_merge_plan(keys_a: List[Index], keys_b: List[Index]):
+    """Literal restatement of flat_map::insert(first, last, collision, nocollision), reference
+    include/blockTensor/flat_map.h:350-425, run on keys only. Returns, for every key of the merged (sorted) list,
+    (key, pa, pb): pa = power of alpha applied to this's element (None if absent), pb = power of alpha applied to the
+    other's element (None if absent). The ideal result is pa = 0, pb = 1 everywhere; the reference's final
+    `for_each(begin(), move_to_end, nocollision)` also hits ORIGINAL elements whose keys are smaller than every key of
+    the other map, so those get pa = 1 (multiplied by alpha) — observed behaviour, reproduced here."""
+    import bisect
+    content = [[k, {"a": 0}] for k in keys_a]           # value = {source: power of alpha}
+    other = [[k, {"b": 0}] for k in keys_b]
+    keyof = lambda lst: [e[0] for e in lst]
+    first, last = 0, len(other)
+    n1 = last - first
+    look = 0
+    for i in range(first, last):
+        look = bisect.bisect_left(keyof(content), other[i][0], look, len(content))
+        if look == len(content):
+            break
+        if not (other[i][0] < content[look][0]):
+            n1 -= 1
+    content.extend([[None, {}] for _ in range(n1)])
+    look = len(content) - n1
+    move_to_end = len(content)
+
+    def nocollision(e):
+        for src in e[1]:
+            e[1][src] += 1
+
+    def collision(x, y):   # a.add_(b, alpha)
+        for src, pw in y[1].items():
+            x[1][src] = pw + 1
+
+    while look != 0 and last != first:
+        ck = keyof(content[:look])
+        la = bisect.bisect_left(keyof(other), content[look - 1][0], first, last)
+        fc = 1 if (la != last and not (content[look - 1][0] < other[la][0])) else 0
+        cnt = last - (la + fc)
+        for t in range(cnt):
+            src = other[last - 1 - t]
+            content[move_to_end - 1 - t] = [src[0], dict(src[1])]
+        old = move_to_end
+        move_to_end -= cnt
+        for e in content[move_to_end:old]:
+            nocollision(e)
+        if fc:
+            move_to_end -= 1
+            look -= 1
+            if move_to_end != look:
+                content[move_to_end] = content[look]
+            collision(content[move_to_end], other[la])
+        last = la
+        if last == first:
+            break
+        lb = bisect.bisect_left(keyof(content[:look]), other[last - 1][0], 0, look)
+        if move_to_end != look:
+            seg = content[lb:look]
+            content[move_to_end - len(seg):move_to_end] = seg
+        move_to_end -= look - lb
+        look = lb
+        fc = 1 if (last != first and not (other[last - 1][0] < content[move_to_end][0])) else 0
+        if fc:
+            collision(content[move_to_end], other[last - 1])
+        last -= fc
+    rem = other[first:last]
+    if rem:
+        assert move_to_end == len(rem)
+        content[move_to_end - len(rem):move_to_end] = [[e[0], dict(e[1])] for e in rem]
+    for e in content[0:move_to_end]:
+        nocollision(e)
+    return [(tuple(k), v.get("a"), v.get("b")) for k, v in content]
+
+
 def add(a: BT, b: BT, alpha: float = 1.0) -> BT:
-    """reference btensor::add / add_, sources/btensor.cpp:2666-2752: sorted merge of the block lists, a + alpha*b on
-    collisions, blocks present on one side only are copied (scaled by alpha when they come from b)."""
+    """reference btensor::add / add_, sources/btensor.cpp:2666-2752: flat_map::merge of the block lists, a + alpha*b
+    on collisions, blocks present on one side only are copied (those of b scaled by alpha). The merge is restated
+    literally (flat_map_merge_plan) because the reference's merge also scales by alpha those blocks of `a` that sort
+    before every block of `b`."""
     assert a.sec_sizes == b.sec_sizes and a.cvals == b.cvals and a.sel == b.sel, "add: structure mismatch"
     out = a.structure_like()
-    for idx, blk in a.blocks.items():
-        out.blocks[idx] = blk.copy()
-    for idx, blk in b.blocks.items():
-        if idx in out.blocks:
-            out.blocks[idx] = out.blocks[idx] + alpha * blk
-        else:
-            out.blocks[idx] = alpha * blk
+    for key, pa, pb in flat_map_merge_plan(sorted(a.blocks), sorted(b.blocks)):
+        v = 0.0
+        if pa is not None:
+            v = v + (alpha ** pa) * a.blocks[key]
+        if pb is not None:
+            v = v + (alpha ** pb) * b.blocks[key]
+        out.blocks[key] = np.array(v, dtype=np.float64, copy=True)
     return out
 
 

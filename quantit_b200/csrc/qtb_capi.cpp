@@ -368,6 +368,10 @@ qtb_status qtb_axpby(qtb_ctx *ctx, double alpha, const qtb_tensor *a, double bet
 {
 	return guarded([&]() { *out = wrap(axpby_dev(ctx->c, nullptr, alpha, *a->t, nullptr, beta, *b->t, false)); });
 }
+qtb_status qtb_add(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double alpha, qtb_tensor **out)
+{
+	return guarded([&]() { *out = wrap(axpby_dev(ctx->c, nullptr, 1.0, *a->t, nullptr, alpha, *b->t, false, alpha)); });
+}
 qtb_status qtb_dot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double *host_out)
 {
 	return guarded(
@@ -431,6 +435,37 @@ qtb_status qtb_two_sites_update(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_t
 {
 	return guarded([&]()
 	               { *psi_out = wrap(two_sites_update(ctx->c, *psi->t, *h2->t, *lenv->t, *renv->t, energy)); });
+}
+
+qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_tensor **mps, int64_t *oc,
+                    const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, double *sweep_energy,
+                    double *sweep_seconds, int64_t *sweep_mid_bond)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx && mpo && mps && oc && options && energy && n_sweeps, QTB_ERR_INVALID_ARGUMENT, "null argument");
+		    std::vector<const Tensor *> H(length);
+		    std::vector<std::unique_ptr<Tensor>> psi(length);
+		    for (int64_t i = 0; i < length; ++i)
+		    {
+			    H[i] = mpo[i]->t.get();
+			    psi[i] = std::move(mps[i]->t); // ownership moves into the sweep and back (also on error)
+		    }
+		    try
+		    {
+			    dmrg(ctx->c, length, H.data(), psi, *oc, *options, *energy, *n_sweeps, sweep_energy, sweep_seconds,
+			         sweep_mid_bond);
+		    }
+		    catch (...)
+		    {
+			    for (int64_t i = 0; i < length; ++i)
+				    mps[i]->t = std::move(psi[i]);
+			    throw;
+		    }
+		    for (int64_t i = 0; i < length; ++i)
+			    mps[i]->t = std::move(psi[i]);
+	    });
 }
 
 } // extern "C"

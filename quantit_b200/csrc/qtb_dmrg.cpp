@@ -1,0 +1,152 @@
+// qtb_dmrg.cpp — the two-site DMRG sweep driver on the engine's primitives.
+//
+// Reference (paths relative to the reference root): sources/dmrg.cpp
+//   dmrg(bMPO&, bMPS&, options, logger)   :92-100      details::dmrg_impl            :219-273
+//   generate_env_impl / trivial edges     :370-409     compute_2sitesHamil_impl      :503-515
+//   sweep                                 :127-142     dmrg_2sites_update::operator() :163-206
+#include <chrono>
+#include <cmath>
+#include <map>
+
+#include "qtb_ops.h"
+
+namespace qtb
+{
+
+static std::unique_ptr<Tensor> trivial_edge(Ctx &ctx, const Tensor &state, i64 sdim, const Tensor &ham, i64 hdim)
+{ // reference generate_env_impl, dmrg.cpp:381-391: ones over (inverse ket leg, inverse MPO leg, ket leg), neutral rule
+	const i64 nc = state.st.ct.nc;
+	Structure st;
+	st.rank = 3;
+	st.ct = state.st.ct;
+	st.sel.assign(nc, 0);
+	auto push = [&](const Tensor &t, i64 d, bool inv)
+	{
+		st.nsec.push_back(t.st.nsec[d]);
+		for (i64 s = 0; s < t.st.nsec[d]; ++s)
+		{
+			st.sec_sizes.push_back(t.st.size_of(d, s));
+			for (i64 c = 0; c < nc; ++c)
+				st.cvals.push_back(inv ? st.ct.norm(-t.st.charge_of(d, s)[c], c) : t.st.charge_of(d, s)[c]);
+		}
+	};
+	push(state, sdim, true);
+	push(ham, hdim, true);
+	push(state, sdim, false);
+	st.finalize();
+	std::vector<i64> index;
+	std::vector<double> data;
+	i64 idx[3];
+	for (idx[0] = 0; idx[0] < st.nsec[0]; ++idx[0])
+		for (idx[1] = 0; idx[1] < st.nsec[1]; ++idx[1])
+			for (idx[2] = 0; idx[2] < st.nsec[2]; ++idx[2])
+				if (st.allowed(idx))
+				{
+					index.insert(index.end(), idx, idx + 3);
+					const i64 n = st.size_of(0, idx[0]) * st.size_of(1, idx[1]) * st.size_of(2, idx[2]);
+					data.insert(data.end(), (size_t)n, 1.0);
+				}
+	return make_tensor(ctx, st, (i64)index.size() / 3, index.data(), data.data());
+}
+
+void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
+          const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
+          i64 *sweep_mid_bond)
+{
+	QTB_REQUIRE(L >= 2, QTB_ERR_INVALID_ARGUMENT, "dmrg: at least two sites are required");
+	for (i64 i = 0; i < L; ++i)
+	{
+		QTB_REQUIRE(mpo[i]->st.rank == 4, QTB_ERR_INVALID_ARGUMENT, "dmrg: MPO tensors must have rank 4");
+		QTB_REQUIRE(mps[i]->st.rank == 3, QTB_ERR_INVALID_ARGUMENT,
+		            "Input bMPT is an invalid bMPS: one or more Tensors has rank differing from 3");
+	}
+	QTB_REQUIRE(oc >= 0 && oc < L, QTB_ERR_INVALID_ARGUMENT,
+	            "orthogonality center position greater than the number of defined tensors.");
+	// environments Env[-1 .. L]
+	std::map<i64, std::unique_ptr<Tensor>> env;
+	env[-1] = trivial_edge(ctx, *mps[0], 0, *mpo[0], 0);
+	env[L] = trivial_edge(ctx, *mps[L - 1], 2, *mpo[L - 1], 2);
+	for (i64 i = 0; i < oc; ++i)
+		env[i] = env_left(ctx, *mpo[i], *mps[i], *env[i - 1]);
+	for (i64 i = L - 1; i > oc; --i)
+		env[i] = env_right(ctx, *mpo[i], *mps[i], *env[i + 1]);
+	// two-site MPO, dmrg.cpp:503-515
+	std::vector<std::unique_ptr<Tensor>> h2(L - 1);
+	for (i64 i = 0; i + 1 < L; ++i)
+	{
+		auto t = tensordot(ctx, *mpo[i], *mpo[i + 1], {2}, {0});
+		h2[i] = permute(*t, {0, 1, 3, 4, 2, 5});
+	}
+	double E0 = 100000.0;
+	const i64 nh = L - 1;
+	const i64 n_step = nh - 1 + (nh == 1 ? 1 : 0);
+	int step = (oc == 0) ? 1 : -1;
+	if (nh == 1)
+		step = 0;
+	const i64 init_pos = oc;
+	QTB_REQUIRE(oc != L - 1 || L == 2, QTB_ERR_RUNTIME,
+	            "dmrg: an orthogonality centre on the last site needs bMPS::move_oc afterwards (not on this path)");
+	if (oc == L - 1)
+		--oc;
+	double *d_scal = (double *)ctx_alloc(ctx, 2 * sizeof(double));
+	n_sweeps = 0;
+	for (i64 it = 0; it < opt.maximum_iterations; ++it)
+	{
+		auto t0 = std::chrono::steady_clock::now();
+		double E = E0;
+		for (i64 s = 0; s < 2 * n_step; ++s)
+		{
+			// ---- dmrg_2sites_update::operator(), dmrg.cpp:163-206 ----
+			auto theta = tensordot(ctx, *mps[oc], *mps[oc + 1], {2}, {0});
+			auto theta2 = two_sites_update(ctx, *theta, *h2[oc], *env[oc - 1], *env[oc + 2], &E);
+			theta.reset();
+			std::unique_ptr<Tensor> u, d, v;
+			block_svd(ctx, *theta2, 2, true, opt.cutoff, opt.minimum_bond, opt.maximum_bond, 2.0, u, d, v);
+			theta2.reset();
+			// d /= sqrt(sum(d^2))
+			{
+				auto dc = conj(*d);
+				dot_dev(ctx, *d, *dc, d_scal, true);
+				if (d->arena->numel > 0)
+					launch_scale(ctx, d->arena->ptr, d->arena->numel, d_scal, 1.0, true);
+			}
+			if (step == 1)
+			{
+				auto vd = mul_lastdim(ctx, *v, *d);
+				auto vdc = conj(*vd);
+				mps[oc] = std::move(u);
+				mps[oc + 1] = permute(*vdc, {2, 0, 1});
+				env[oc] = env_left(ctx, *mpo[oc], *mps[oc], *env[oc - 1]);
+			}
+			else
+			{
+				auto vc = conj(*v);
+				mps[oc] = mul_lastdim(ctx, *u, *d);
+				mps[oc + 1] = permute(*vc, {2, 0, 1});
+				env[oc + 1] = env_right(ctx, *mpo[oc + 1], *mps[oc + 1], *env[oc + 2]);
+			}
+			oc += step;
+			if (oc == 0 || oc == L - 2)
+				step = -step;
+		}
+		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+		const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (sweep_energy)
+			sweep_energy[it] = E;
+		if (sweep_seconds)
+			sweep_seconds[it] = secs;
+		if (sweep_mid_bond)
+			sweep_mid_bond[it] = mps[L / 2]->st.dim_size(0);
+		n_sweeps = it + 1;
+		const double Eold = E0;
+		E0 = E;
+		if (!(std::fabs((E0 - Eold) / E0) > opt.convergence_criterion)) // stops on NaN too (dmrg.cpp:247-254)
+			break;
+	}
+	ctx_free(ctx, d_scal);
+	QTB_REQUIRE(oc == init_pos || (init_pos == L - 1), QTB_ERR_RUNTIME,
+	            "the orthogonality center finished somewhere surprising!");
+	energy = E0;
+}
+
+} // namespace qtb

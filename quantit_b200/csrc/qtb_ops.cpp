@@ -30,7 +30,8 @@ static const Tensor &packed(Ctx &ctx, const Tensor &t, std::unique_ptr<Tensor> &
 }
 
 std::unique_ptr<Tensor> axpby_dev(Ctx &ctx, const double *ca_ptr, double ca_mul, const Tensor &a_in,
-                                  const double *cb_ptr, double cb_mul, const Tensor &b_in, bool divide_a)
+                                  const double *cb_ptr, double cb_mul, const Tensor &b_in, bool divide_a,
+                                  double merge_quirk)
 {
 	require_same_structure(a_in, b_in, "add");
 	std::unique_ptr<Tensor> ha, hb;
@@ -73,6 +74,10 @@ std::unique_ptr<Tensor> axpby_dev(Ctx &ctx, const double *ca_ptr, double ca_mul,
 		VecSeg s{};
 		s.n = out->block_numel(ob);
 		s.o_off = out->offs[ob];
+		s.a_scale = 1.0;
+		if (merge_quirk != 1.0 && src[ob].first >= 0 &&
+		    (b.nblocks == 0 || std::lexicographical_compare(out->idx(ob), out->idx(ob) + r, b.idx(0), b.idx(0) + r)))
+			s.a_scale = merge_quirk; // reference flat_map::insert: elements of `this` below other's first key
 		s.a_off = src[ob].first >= 0 ? a.offs[src[ob].first] : -1;
 		s.b_off = src[ob].second >= 0 ? b.offs[src[ob].second] : -1;
 		if (src[ob].first >= 0)
@@ -113,6 +118,7 @@ void dot_dev(Ctx &ctx, const Tensor &a_in, const Tensor &b_in, double *d_result,
 			s.a_off = a.offs[i];
 			s.b_off = b.offs[j];
 			s.o_off = 0;
+			s.a_scale = 1.0;
 			if (s.n)
 				segs.push_back(s);
 			++i;
@@ -213,7 +219,8 @@ std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tens
 	auto phi = heff_apply(ctx, psi, h2, lenv, renv);
 	auto psic = conj(psi);
 	dot_dev(ctx, *phi, *psic, scal + 0, false);                                // a0 = <phi, psi>
-	auto phi2 = axpby_dev(ctx, nullptr, 1.0, *phi, scal + 0, -1.0, psi, false); // phi -= a0*psi
+	// psi_ip -= state * a0  ==  psi_ip.add_(state*a0, -1) (btensor.h:473): with the reference's merge behaviour
+	auto phi2 = axpby_dev(ctx, nullptr, 1.0, *phi, scal + 0, -1.0, psi, false, -1.0);
 	phi.reset();
 	auto phi2c = conj(*phi2);
 	dot_dev(ctx, *phi2, *phi2c, scal + 1, true); // b = sqrt(<phi,phi>)

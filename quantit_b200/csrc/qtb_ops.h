@@ -9,8 +9,11 @@ namespace qtb
 {
 // out = (ca)*a + (cb)*b over the union of the block lists; coefficients = (*ptr or 1) * mul, read on the device.
 // divide_a: a's term is a / ca instead of ca * a.
+// merge_quirk != 1: reproduces the reference's flat_map::merge behaviour (flat_map.h:350-425, last for_each): the blocks
+// of `a` that sort before every block of `b` are additionally multiplied by the add_ coefficient (= merge_quirk).
 std::unique_ptr<Tensor> axpby_dev(Ctx &ctx, const double *ca_ptr, double ca_mul, const Tensor &a,
-                                  const double *cb_ptr, double cb_mul, const Tensor &b, bool divide_a);
+                                  const double *cb_ptr, double cb_mul, const Tensor &b, bool divide_a,
+                                  double merge_quirk = 1.0);
 void dot_dev(Ctx &ctx, const Tensor &a, const Tensor &b, double *d_result, bool take_sqrt);
 std::unique_ptr<Tensor> mul_lastdim(Ctx &ctx, const Tensor &a, const Tensor &d);
 std::unique_ptr<Tensor> heff_apply(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,
@@ -22,4 +25,8 @@ std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tens
 // qtb_svd.cu
 void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size,
                double pow, std::unique_ptr<Tensor> &u, std::unique_ptr<Tensor> &d, std::unique_ptr<Tensor> &v);
+// qtb_dmrg.cpp
+void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
+          const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
+          i64 *sweep_mid_bond);
 } // namespace qtb

@@ -80,7 +80,7 @@ __global__ void axpby_kernel(const VecSeg *__restrict__ segs, const VecWork *__r
 		{
 			double v = 0.0;
 			if (s.a_off >= 0)
-				v = divide_a ? a[s.a_off + e] / ca : ca * a[s.a_off + e];
+				v = (divide_a ? a[s.a_off + e] / ca : ca * a[s.a_off + e]) * s.a_scale;
 			if (s.b_off >= 0)
 				v += cb * b[s.b_off + e];
 			out[s.o_off + e] = v;

@@ -26,6 +26,7 @@ struct GatherWork
 struct VecSeg
 {
 	i64 a_off, b_off, o_off, n; // a_off / b_off < 0: operand absent on this segment
+	double a_scale;             // extra factor on the a term of this segment (1 except for the reference's merge quirk)
 };
 struct VecWork
 {

@@ -95,6 +95,7 @@ _SIGS = [
                                      i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64,
                                      i64, p_i64, p_i64, p_i64, p_i64, p_i64, p_f64]),
     ("qtb_axpby", C.c_int, [vp, C.c_double, vp, C.c_double, vp, C.POINTER(vp)]),
+    ("qtb_add", C.c_int, [vp, vp, vp, C.c_double, C.POINTER(vp)]),
     ("qtb_dot", C.c_int, [vp, vp, vp, p_f64]),
     ("qtb_scale_", C.c_int, [vp, vp, C.c_double]),
     ("qtb_mul_lastdim", C.c_int, [vp, vp, vp, C.POINTER(vp)]),
@@ -104,8 +105,14 @@ _SIGS = [
     ("qtb_env_left", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_env_right", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_two_sites_update", C.c_int, [vp, vp, vp, vp, vp, p_f64, C.POINTER(vp)]),
+    ("qtb_dmrg", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, p_f64, p_f64, p_i64]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
+
+
+class DmrgOptionsC(C.Structure):
+    _fields_ = [("cutoff", C.c_double), ("convergence_criterion", C.c_double), ("maximum_bond", C.c_int64),
+                ("minimum_bond", C.c_int64), ("maximum_iterations", C.c_int64)]
 
 _lib = None
 
@@ -340,8 +347,9 @@ class BTensor:
         return BTensor(self.ctx, h)
 
     def add(self, other: "BTensor", alpha: float = 1.0) -> "BTensor":
+        """reference btensor::add(other, alpha), btensor.cpp:2666 (including its merge behaviour, see qtb.h)"""
         h = vp()
-        _check(self.ctx.lib.qtb_axpby(self.ctx.h, 1.0, self.h, float(alpha), other.h, C.byref(h)))
+        _check(self.ctx.lib.qtb_add(self.ctx.h, self.h, other.h, float(alpha), C.byref(h)))
         return BTensor(self.ctx, h)
 
     def axpby(self, alpha: float, other: "BTensor", beta: float) -> "BTensor":
@@ -407,6 +415,41 @@ def two_sites_update(state: BTensor, hamil: BTensor, lenv: BTensor, renv: BTenso
     e = C.c_double()
     _check(state.ctx.lib.qtb_two_sites_update(state.ctx.h, state.h, hamil.h, lenv.h, renv.h, C.byref(e), C.byref(h)))
     return e.value, BTensor(state.ctx, h)
+
+
+class dmrg_options:
+    """reference include/dmrg_options.h:15-58 (same field names and defaults)"""
+
+    def __init__(self, cutoff: float = 1e-6, convergence_criterion: float = 1e-5, maximum_bond: Optional[int] = None,
+                 minimum_bond: int = 4, maximum_iterations: int = 1000):
+        self.cutoff = cutoff
+        self.convergence_criterion = convergence_criterion
+        self.maximum_bond = maximum_bond
+        self.minimum_bond = minimum_bond
+        self.maximum_iterations = maximum_iterations
+
+
+def dmrg(hamiltonian: List[BTensor], in_out_state: List[BTensor], options: dmrg_options, oc: int = 0, log: Optional[dict] = None):
+    """reference quantit::dmrg(bMPO&, bMPS&, const dmrg_options&, dmrg_logger&), dmrg.h:39: optimises `in_out_state`
+    in place (the list's BTensor handles are updated) and returns the energy. `log`, if given, receives per-sweep
+    energies / seconds / mid-chain bond dimension (what dmrg_log_sweeptime records)."""
+    ctx = in_out_state[0].ctx
+    L = len(hamiltonian)
+    H = (vp * L)(*[t.h for t in hamiltonian])
+    P = (vp * L)(*[t.h for t in in_out_state])
+    o = DmrgOptionsC(options.cutoff, options.convergence_criterion,
+                     -1 if options.maximum_bond is None else int(options.maximum_bond), int(options.minimum_bond),
+                     int(options.maximum_iterations))
+    n = int(options.maximum_iterations)
+    se, ss, sb = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    E, ns, occ = C.c_double(), i64(), i64(oc)
+    _check(ctx.lib.qtb_dmrg(ctx.h, L, H, P, C.byref(occ), C.byref(o), C.byref(E), C.byref(ns), se, ss, sb))
+    if log is not None:
+        log["energy"] = [se[i] for i in range(ns.value)]
+        log["seconds"] = [ss[i] for i in range(ns.value)]
+        log["mid_bond"] = [sb[i] for i in range(ns.value)]
+        log["oc"] = occ.value
+    return E.value
 
 
 def tensordot_host(a: dict, b: dict, dims_a, dims_b, ctx: Optional[Context] = None):

@@ -85,6 +85,21 @@ def main():
     run("svdt", ft, 2, 1e-4, 4, 18, 2, *(os.path.join(HERE, f"svdt_{x}.qtbt") for x in "UdV"))
     run("svdt", ft, 2, 1e-1, 1, 1000, 2, *(os.path.join(HERE, f"svdt2_{x}.qtbt") for x in "UdV"))
     run("svdt", ft, 2, 0.5, 1, 1000, 2, *(os.path.join(HERE, f"svdt3_{x}.qtbt") for x in "UdV"))  # drops whole sectors
+    # ---- whole two-site DMRG: MPO + initial MPS dumped by the reference, its per-sweep energies, its final MPS ----
+    import json
+    for name, cmd, L, maxbond in [("dmrg_heis8", "heis", 8, 30), ("dmrg_hub4", "hub", 4, 40)]:
+        d = os.path.join(HERE, name)
+        os.makedirs(d, exist_ok=True)
+        out = subprocess.run([H, cmd, str(L), str(maxbond), "1e-10", "1e-9", "12", "0", d], capture_output=True, text=True,
+                             check=True).stdout
+        rec = {"L": L, "maximum_bond": maxbond, "cutoff": 1e-10, "convergence_criterion": 1e-9, "minimum_bond": 4,
+               "maximum_iterations": 12,
+               "sweep_energy": [float(l.split()[3]) for l in out.splitlines() if l.startswith("SWEEP")],
+               "mid_bond": [int(l.split()[5]) for l in out.splitlines() if l.startswith("SWEEP")],
+               "E0": [float(l.split()[1]) for l in out.splitlines() if l.startswith("E0")][0],
+               "contract_E": [float(l.split()[1]) for l in out.splitlines() if l.startswith("CONTRACT_E")][0],
+               "oc": [int(l.split()[1]) for l in out.splitlines() if l.startswith("OC")][0]}
+        json.dump(rec, open(os.path.join(d, "reference_run.json"), "w"), indent=1)
     tot = sum(os.path.getsize(os.path.join(HERE, x)) for x in os.listdir(HERE) if x.endswith(".qtbt"))
     print("golden fixtures written,", tot, "bytes")
 

@@ -96,3 +96,29 @@ def test_heff_env_update_golden(engine):
     E, p = qb.two_sites_update(psi, H2, L, R)
     assert abs(E - g("update_E").item()) <= 1e-12 * abs(E)
     assert_same(back(p), g("update_psi"), 1e-12)
+
+
+@pytest.mark.parametrize("name", ["dmrg_heis8", "dmrg_hub4"])
+def test_dmrg_against_reference_run(engine, name):
+    """whole two-site DMRG (U(1) Heisenberg L=8; U(1)xU(1) Hubbard L=4): same MPO and initial MPS as the reference run
+    (dumped by oracle/_ref/ref_harness), energies per sweep to 1e-10 relative, identical final block structure"""
+    import json
+    qb = engine
+    d = os.path.join(G, name)
+    rec = json.load(open(os.path.join(d, "reference_run.json")))
+    L = rec["L"]
+    H = [eng(qb, orc.read_qtbt(os.path.join(d, f"H_{i}.qtbt"))) for i in range(L)]
+    psi = [eng(qb, orc.read_qtbt(os.path.join(d, f"psi0_{i}.qtbt"))) for i in range(L)]
+    log = {}
+    opt = qb.dmrg_options(rec["cutoff"], rec["convergence_criterion"], rec["maximum_bond"], rec["minimum_bond"],
+                          rec["maximum_iterations"])
+    E = qb.dmrg(H, psi, opt, oc=rec["oc"], log=log)
+    assert len(log["energy"]) == len(rec["sweep_energy"])
+    assert np.allclose(log["energy"], rec["sweep_energy"], rtol=1e-10, atol=0), (log["energy"], rec["sweep_energy"])
+    assert abs(E - rec["E0"]) <= 1e-10 * abs(rec["E0"])
+    assert log["mid_bond"] == rec["mid_bond"]
+    for i in range(L):
+        want = orc.read_qtbt(os.path.join(d, f"psiF_{i}.qtbt"))
+        got = back(psi[i])
+        assert got.sec_sizes == want.sec_sizes and got.cvals == want.cvals and got.sel == want.sel, i
+        assert sorted(got.blocks) == sorted(want.blocks), i

@@ -149,3 +149,15 @@ def test_heff_and_envs(engine):
     t = orc.tensordot(t, oH2, [0, 2, 3], [0, 4, 5])
     t = orc.tensordot(t, to_oracle(R), [1, 4], [0, 1])
     check_same(out, t)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_add_matches_reference_merge(engine, seed):
+    """btensor::add(other, alpha) including the reference's flat_map::merge behaviour (see include/qtb.h qtb_add)"""
+    rng = np.random.default_rng(700 + seed)
+    sh = wl.random_btensor(rng, int(rng.integers(1, 4)), max_sec=4, fill=1.0)
+    keys = list(sh["blocks"])
+    a = dict(sh, blocks={k: sh["blocks"][k] for k in keys if rng.random() < 0.6})
+    b = dict(sh, blocks={k: rng.standard_normal(sh["blocks"][k].shape) for k in keys if rng.random() < 0.6})
+    alpha = float(rng.choice([-1.0, 0.5, 2.0]))
+    check_same(to_engine(engine, a).add(to_engine(engine, b), alpha), orc.add(to_oracle(a), to_oracle(b), alpha))
