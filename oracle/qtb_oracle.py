@@ -689,7 +689,7 @@ def two_sites_update(state: BT, hamil: BT, lenv: BT, renv: BT):
     """one_step_lanczos_impl + two_sites_update_impl, dmrg.cpp:584-638. Returns (E, updated state)."""
     psi_ip = hamil2site_times_state(state, hamil, lenv, renv)
     a0 = dot_all(psi_ip, conj(state))
-    psi_ip = add(psi_ip, state, -a0)
+    psi_ip = add(psi_ip, mul_bcast(state, scalar(a0, state.nc, state.mods)), -1.0)  # psi_ip -= state * a0
     b = float(np.sqrt(dot_all(psi_ip, conj(psi_ip))))
     if abs(b) >= 1e-15:
         for k in psi_ip.blocks:
