@@ -5,6 +5,8 @@
 //   generate_env_impl / trivial edges     :370-409     compute_2sitesHamil_impl      :503-515
 //   sweep                                 :127-142     dmrg_2sites_update::operator() :163-206
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <map>
 
@@ -90,6 +92,18 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 		--oc;
 	double *d_scal = (double *)ctx_alloc(ctx, 2 * sizeof(double));
 	n_sweeps = 0;
+	// QTB_PROFILE=1: per-phase wall time with a stream sync after every phase (diagnostics only, perturbs the timing)
+	const bool prof = std::getenv("QTB_PROFILE") != nullptr;
+	double tph[5] = {0, 0, 0, 0, 0};
+	auto tick = [&](int ph, std::chrono::steady_clock::time_point &t)
+	{
+		if (!prof)
+			return;
+		cudaStreamSynchronize(ctx.stream);
+		auto now = std::chrono::steady_clock::now();
+		tph[ph] += std::chrono::duration<double, std::milli>(now - t).count();
+		t = now;
+	};
 	for (i64 it = 0; it < opt.maximum_iterations; ++it)
 	{
 		auto t0 = std::chrono::steady_clock::now();
@@ -97,12 +111,16 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 		for (i64 s = 0; s < 2 * n_step; ++s)
 		{
 			// ---- dmrg_2sites_update::operator(), dmrg.cpp:163-206 ----
+			auto tp = std::chrono::steady_clock::now();
 			auto theta = tensordot(ctx, *mps[oc], *mps[oc + 1], {2}, {0});
+			tick(0, tp);
 			auto theta2 = two_sites_update(ctx, *theta, *h2[oc], *env[oc - 1], *env[oc + 2], &E);
 			theta.reset();
+			tick(1, tp);
 			std::unique_ptr<Tensor> u, d, v;
 			block_svd(ctx, *theta2, 2, true, opt.cutoff, opt.minimum_bond, opt.maximum_bond, 2.0, u, d, v);
 			theta2.reset();
+			tick(2, tp);
 			// d /= sqrt(sum(d^2))
 			{
 				auto dc = conj(*d);
@@ -125,9 +143,16 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 				mps[oc + 1] = permute(*vc, {2, 0, 1});
 				env[oc + 1] = env_right(ctx, *mpo[oc + 1], *mps[oc + 1], *env[oc + 2]);
 			}
+			tick(3, tp);
 			oc += step;
 			if (oc == 0 || oc == L - 2)
 				step = -step;
+		}
+		if (prof)
+		{
+			std::fprintf(stderr, "[qtb profile] sweep %ld: theta %.1f ms, lanczos %.1f ms, svd %.1f ms, absorb+env %.1f ms; plans built %ld, cache hits %ld, launches %ld\n",
+			             (long)it, tph[0], tph[1], tph[2], tph[3], (long)ctx.counters[2], (long)ctx.counters[3], (long)ctx.counters[0]);
+			tph[0] = tph[1] = tph[2] = tph[3] = 0;
 		}
 		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
 		const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

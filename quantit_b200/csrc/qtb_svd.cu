@@ -24,6 +24,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -35,9 +37,10 @@ namespace qtb
 
 namespace
 {
-constexpr int kJB = 16;       // column-block width of the outer block Jacobi
+constexpr int kJB = 32;       // column-block width of the outer block Jacobi
 constexpr int kPMax = 2 * kJB; // max panel width
 constexpr int kMaxSweeps = 40;
+constexpr size_t kEigSmem = 2 * kPMax * (kPMax + 1) * sizeof(double);
 
 struct SvdGroup
 { // device-side description of one charge group's workspace
@@ -114,18 +117,24 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const SvdGroup *__restric
                                                         const SvdItem *__restrict__ items, const double *__restrict__ X,
                                                         double *__restrict__ gram, unsigned long long *offmax)
 {
-	constexpr int CH = 64; // rows per chunk
+	constexpr int CH = 32;          // rows per chunk
+	constexpr int T = kPMax / 16;   // micro-tile edge: 16x16 threads cover the kPMax x kPMax Gram matrix
 	__shared__ double sP[CH][kPMax + 1];
+	__shared__ double sdiag[kPMax];
 	const SvdItem it = items[blockIdx.x];
 	const SvdGroup G = groups[it.group];
 	const int wi = block_width(G, it.bi), wj = block_width(G, it.bj), p = wi + wj;
-	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4; // G(ty*2+{0,1}, tx*2+{0,1})
-	double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+	const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+	double acc[T][T];
+#pragma unroll
+	for (int i = 0; i < T; ++i)
+#pragma unroll
+		for (int j = 0; j < T; ++j)
+			acc[i][j] = 0.0;
 	const double *Xg = X + G.x_off;
 	for (int r0 = 0; r0 < G.m; r0 += CH)
 	{
 		const int nr = min(CH, G.m - r0);
-		// load chunk: column c of the panel is a contiguous run of the column-major X
 		for (int e = threadIdx.x; e < CH * kPMax; e += 256)
 		{
 			const int c = e / CH, r = e % CH;
@@ -138,44 +147,51 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const SvdGroup *__restric
 			sP[r][c] = v;
 		}
 		__syncthreads();
-#pragma unroll 8
+#pragma unroll 4
 		for (int r = 0; r < CH; ++r)
 		{
-			const double x0 = sP[r][ty * 2], x1 = sP[r][ty * 2 + 1], y0 = sP[r][tx * 2], y1 = sP[r][tx * 2 + 1];
-			a00 += x0 * y0;
-			a01 += x0 * y1;
-			a10 += x1 * y0;
-			a11 += x1 * y1;
+			double x[T], y[T];
+#pragma unroll
+			for (int i = 0; i < T; ++i)
+			{
+				x[i] = sP[r][ty * T + i];
+				y[i] = sP[r][tx * T + i];
+			}
+#pragma unroll
+			for (int i = 0; i < T; ++i)
+#pragma unroll
+				for (int j = 0; j < T; ++j)
+					acc[i][j] += x[i] * y[j];
 		}
 		__syncthreads();
 	}
 	double *Gm = gram + (size_t)blockIdx.x * kPMax * kPMax;
-	Gm[(ty * 2) * kPMax + tx * 2] = a00;
-	Gm[(ty * 2) * kPMax + tx * 2 + 1] = a01;
-	Gm[(ty * 2 + 1) * kPMax + tx * 2] = a10;
-	Gm[(ty * 2 + 1) * kPMax + tx * 2 + 1] = a11;
-	// convergence gauge: needs the diagonal -> stage the diagonal through shared memory
-	__shared__ double sdiag[kPMax];
+#pragma unroll
+	for (int i = 0; i < T; ++i)
+#pragma unroll
+		for (int j = 0; j < T; ++j)
+			Gm[(ty * T + i) * kPMax + tx * T + j] = acc[i][j];
 	if (ty == tx)
 	{
-		sdiag[ty * 2] = a00;
-		sdiag[ty * 2 + 1] = a11;
+#pragma unroll
+		for (int i = 0; i < T; ++i)
+			sdiag[ty * T + i] = acc[i][i];
 	}
 	__syncthreads();
 	double loc = 0.0;
-	auto gauge = [&](double g, int i, int j)
-	{
-		if (i < j && j < p)
+#pragma unroll
+	for (int i = 0; i < T; ++i)
+#pragma unroll
+		for (int j = 0; j < T; ++j)
 		{
-			const double dd = sdiag[i] * sdiag[j];
-			if (dd > 0.0)
-				loc = fmax(loc, fabs(g) / sqrt(dd));
+			const int gi = ty * T + i, gj = tx * T + j;
+			if (gi < gj && gj < p)
+			{
+				const double dd = sdiag[gi] * sdiag[gj];
+				if (dd > 0.0)
+					loc = fmax(loc, fabs(acc[i][j]) / sqrt(dd));
+			}
 		}
-	};
-	gauge(a00, ty * 2, tx * 2);
-	gauge(a01, ty * 2, tx * 2 + 1);
-	gauge(a10, ty * 2 + 1, tx * 2);
-	gauge(a11, ty * 2 + 1, tx * 2 + 1);
 	for (int o = 16; o > 0; o >>= 1)
 		loc = fmax(loc, __shfl_xor_sync(0xffffffffu, loc, o));
 	if ((threadIdx.x & 31) == 0 && loc > 0.0)
@@ -189,8 +205,9 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const SvdGroup *__restric
 __global__ void __launch_bounds__(256) svd_eig_kernel(const SvdGroup *__restrict__ groups,
                                                        const SvdItem *__restrict__ items, double *__restrict__ gram)
 {
-	__shared__ double sG[kPMax][kPMax + 1];
-	__shared__ double sJ[kPMax][kPMax + 1];
+	extern __shared__ double eig_smem[];
+	double(*sG)[kPMax + 1] = reinterpret_cast<double(*)[kPMax + 1]>(eig_smem);
+	double(*sJ)[kPMax + 1] = reinterpret_cast<double(*)[kPMax + 1]>(eig_smem + kPMax * (kPMax + 1));
 	__shared__ double sc[kPMax / 2], ss[kPMax / 2];
 	__shared__ int sp[kPMax / 2], sq[kPMax / 2];
 	__shared__ int s_rot;
@@ -336,6 +353,142 @@ __global__ void __launch_bounds__(128) svd_update_kernel(const SvdGroup *__restr
 			Xg[(i64)col * G.ld] = acc;
 		}
 	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// panel: the three kernels above fused for panels that fit in shared memory ((m+n) x p doubles): the (m+n) x (wI+wJ)
+// panel of [A;V] is loaded once, orthogonalised in place by one-sided (Hestenes) Jacobi rotations among its columns —
+// one warp per column pair, 16 disjoint pairs per round, round-robin over the <= 32 columns — and written back.
+// No Gram matrix is formed at all in this regime (bond dimension up to a few hundred): the rotation angles come from
+// three warp-reduced dot products of the columns themselves.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPanelThreads = 1024; // 32 warps = one per disjoint pair of a 64-column round
+constexpr int kPanelInner = 3;      // at most this many inner sweeps per visit (stops as soon as a sweep rotates nothing)
+
+// 1/sqrt(x) to full double precision from the single-precision MUFU estimate + 2 Newton steps (the fp64 sqrt/div
+// sequences are the critical path of a rotation; the rotation stays orthogonal to rounding whatever t's accuracy is)
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+	double y = (double)rsqrtf((float)x);
+	y = y * (1.5 - 0.5 * x * y * y);
+	y = y * (1.5 - 0.5 * x * y * y);
+	return y;
+}
+
+__global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup *__restrict__ groups,
+                                                                   const SvdItem *__restrict__ items,
+                                                                   double *__restrict__ X, unsigned long long *offmax)
+{
+	extern __shared__ double sp[];
+	__shared__ int s_rot;
+	const SvdItem it = items[blockIdx.x];
+	const SvdGroup G = groups[it.group];
+	const int wi = block_width(G, it.bi), wj = block_width(G, it.bj), p = wi + wj;
+	const int nrows = G.m + G.n;
+	const int ld = nrows | 1; // odd leading dimension: lanes walking a column never collide, columns are skewed
+	double *Xg = X + G.x_off;
+	auto gcol = [&](int c) { return c < wi ? it.bi * kJB + c : it.bj * kJB + (c - wi); };
+	for (int e = threadIdx.x; e < p * nrows; e += kPanelThreads)
+	{
+		const int c = e / nrows, r = e - c * nrows;
+		sp[c * ld + r] = Xg[(i64)gcol(c) * G.ld + r];
+	}
+	if (threadIdx.x == 0)
+		s_rot = 0;
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int pe = (p + 1) & ~1;
+	double worst = 0.0;
+	const double rot_tol = 2.3e-16 * sqrt((double)G.m);
+	const double rot_tol2 = rot_tol * rot_tol;
+	// a panel that holds the whole matrix is driven to convergence here; otherwise a few inner sweeps per visit
+	const int max_inner = (G.nb <= 2) ? 30 : kPanelInner;
+	for (int sweep = 0; sweep < max_inner; ++sweep)
+	{
+		for (int step = 0; step < pe - 1; ++step)
+		{
+			if (warp < pe / 2)
+			{
+				int a, b;
+				if (warp == 0)
+				{
+					a = pe - 1;
+					b = step;
+				}
+				else
+				{
+					a = (step + warp) % (pe - 1);
+					b = (step - warp + (pe - 1)) % (pe - 1);
+				}
+				const int ci = min(a, b), cj = max(a, b);
+				if (cj < p)
+				{
+					double *x = sp + ci * ld, *y = sp + cj * ld;
+					double al = 0.0, be = 0.0, ga = 0.0;
+					for (int r = lane; r < G.m; r += 32)
+					{
+						const double xv = x[r], yv = y[r];
+						al += xv * xv;
+						be += yv * yv;
+						ga += xv * yv;
+					}
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1)
+					{
+						al += __shfl_xor_sync(0xffffffffu, al, o);
+						be += __shfl_xor_sync(0xffffffffu, be, o);
+						ga += __shfl_xor_sync(0xffffffffu, ga, o);
+					}
+					const double dd = al * be;
+					// rotate when |ga| > tol sqrt(al be); gauge (first inner sweep only) = |ga|/sqrt(al be)
+					const bool rot = dd > 0.0 && ga * ga > rot_tol2 * dd;
+					double cs = 1.0, sn = 0.0;
+					if (rot)
+					{
+						if (sweep == 0)
+							worst = fmax(worst, fabs(ga) * fast_rsqrt(dd));
+						if (lane == 0)
+							s_rot = 1; // benign race: every writer stores 1
+						// angle in full double precision: on graded matrices (singular values spanning 1e-30 and more,
+						// every truncated DMRG theta) t underflows single precision and the sweep would never converge
+						const double zeta = (be - al) / (2.0 * ga);
+						const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+						cs = fast_rsqrt(1.0 + t * t);
+						sn = cs * t;
+					}
+					// de Rijk ordering: the column with the larger norm ends up first (a swap is an orthogonal
+					// transformation too); graded matrices — every DMRG theta — converge in far fewer sweeps.
+					// al_new - be_new = (cs^2 - sn^2)(al - be) - 4 cs sn ga
+					const bool swap = ((cs * cs - sn * sn) * (al - be) - 4.0 * cs * sn * ga) < 0.0;
+					if (rot || swap)
+					{
+						for (int r = lane; r < nrows; r += 32)
+						{
+							const double xv = x[r], yv = y[r];
+							const double xn = cs * xv - sn * yv, yn = sn * xv + cs * yv;
+							x[r] = swap ? yn : xn;
+							y[r] = swap ? xn : yn;
+						}
+					}
+				}
+			}
+			__syncthreads();
+		}
+		const int rotated = s_rot;
+		__syncthreads();
+		if (!rotated)
+			break;
+		if (threadIdx.x == 0)
+			s_rot = 0;
+		__syncthreads();
+	}
+	for (int e = threadIdx.x; e < p * nrows; e += kPanelThreads)
+	{
+		const int c = e / nrows, r = e - c * nrows;
+		Xg[(i64)gcol(c) * G.ld + r] = sp[c * ld + r];
+	}
+	if (lane == 0 && worst > 0.0)
+		atomicMax(offmax, (unsigned long long)__double_as_longlong(worst));
 }
 
 // column norms of the A part: sigma[perm_off + j]
@@ -678,6 +831,21 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				for (i64 g = 0; g < ng; ++g)
 					max_m = std::max(max_m, dg[g].m);
 				const double conv_tol = 1e-14 + 4.5e-16 * std::sqrt((double)max_m);
+				// panels that fit in shared memory take the fused Hestenes kernel
+				const size_t panel_smem = (size_t)((max_rows | 1)) * kPMax * sizeof(double);
+				static bool panel_attr_set = false;
+				const bool use_panel = panel_smem <= 220 * 1024;
+				static bool eig_attr_set = false;
+				if (!use_panel && !eig_attr_set)
+				{
+					QTB_CUDA(cudaFuncSetAttribute(svd_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEigSmem));
+					eig_attr_set = true;
+				}
+				if (use_panel && !panel_attr_set)
+				{
+					QTB_CUDA(cudaFuncSetAttribute(svd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+					panel_attr_set = true;
+				}
 				for (int sweep = 0; sweep < kMaxSweeps; ++sweep)
 				{
 					for (int t = 0; t < period_max; ++t)
@@ -686,8 +854,14 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 						if (cnt == 0)
 							continue;
 						const SvdItem *its = d_items + step_begin[t];
+						if (use_panel)
+						{
+							svd_panel_kernel<<<cnt, kPanelThreads, panel_smem, ctx.stream>>>(d_groups, its, X, d_off + sweep);
+							ctx.counters[0] += 1;
+							continue;
+						}
 						svd_gram_kernel<<<cnt, 256, 0, ctx.stream>>>(d_groups, its, X, d_gram, d_off + sweep);
-						svd_eig_kernel<<<cnt, 256, 0, ctx.stream>>>(d_groups, its, d_gram);
+						svd_eig_kernel<<<cnt, 256, kEigSmem, ctx.stream>>>(d_groups, its, d_gram);
 						dim3 ug((max_rows + 127) / 128, cnt);
 						svd_update_kernel<<<ug, 128, 0, ctx.stream>>>(d_groups, its, X, d_gram);
 						ctx.counters[0] += 3;
@@ -698,6 +872,9 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					QTB_CUDA(cudaStreamSynchronize(ctx.stream));
 					double off;
 					std::memcpy(&off, &bits, sizeof(off));
+					if (std::getenv("QTB_SVD_DEBUG"))
+						std::fprintf(stderr, "[qtb svd] sweep %d gauge %.3e (tol %.3e) groups %ld steps %d panel %d\n", sweep, off,
+						             conv_tol, (long)ng, period_max, (int)use_panel);
 					if (off < conv_tol)
 						break;
 				}
