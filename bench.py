@@ -45,6 +45,9 @@ WORKLOAD_DESC = {
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled through NVML every 2 ms while the timed region runs (nvidia-smi takes
+    ~100 ms per query, longer than the whole timed region of a 70 us step)."""
+
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu = gpu_index
@@ -52,30 +55,39 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self._halt = threading.Event()
         self.max_mhz = None
+        self.err = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                     "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._halt.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in names.items():
+                    if mask & bit:
                         self.reasons.add(n)
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+                self._halt.wait(0.002)
+        except Exception as e:  # keep the bench alive; the record says why there are no samples
+            self.err = repr(e)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def dump_qtbt(desc, path):
@@ -260,7 +272,7 @@ def time_e2e(torch, qb, ctx, w, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="T1", choices=list(WORKLOADS))
