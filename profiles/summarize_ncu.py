@@ -1,0 +1,36 @@
+"""Reads .ncu-rep files (ncu -i ... --page raw --csv) and writes the metrics the roofline numbers come from as CSV.
+usage: python profiles/summarize_ncu.py out.csv rep1.ncu-rep [rep2 ...]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.min.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.max.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__shared_mem_per_block_dynamic", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "lts__t_sector_hit_rate.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
+
+out = csv.writer(open(sys.argv[1], "w", newline=""))
+out.writerow(["report", "launch", "kernel", "metric", "unit", "value"])
+for rep in sys.argv[2:]:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        kern = r[hdr.index("Kernel Name")].split("(")[0][:80]
+        for i, h in enumerate(hdr):
+            if h in KEEP:
+                out.writerow([rep.split("/")[-1], r[hdr.index("ID")], kern, h, units[i], r[i]])
