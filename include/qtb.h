@@ -58,6 +58,23 @@ void *qtb_ctx_stream(qtb_ctx *ctx);
  * [6] algorithmic GEMM flops issued (sum 2mnk), [7] device bytes currently allocated */
 qtb_status qtb_ctx_counters(qtb_ctx *ctx, int64_t out[8]);
 
+/* ---- charge-sector sharding across the GPUs of one node (no reference counterpart: the reference
+ * is single-process, its only parallelism is the BLAS threading inside libtorch) -----------------------------------
+ * One process (one qtb_ctx) per GPU, all ranks hold the SAME tensors (MPS, environments, MPO) and make the SAME calls.
+ * With world > 1 the engine computes, on each rank, only the output blocks that rank owns — charge sectors of one
+ * designated leg of the result, assigned by a longest-processing-time-first balance of the planner's flop counts —
+ * for H_eff.psi (qtb_heff_apply, qtb_two_sites_update), the environment updates, the two-site theta inside qtb_dmrg
+ * and the charge groups of the block SVD; the pieces are then summed into every rank's (zero-filled) full arena by ONE
+ * collective per result. Adding zeros is exact, so an N-GPU run is bit-identical to the 1-GPU run.
+ * The collective is supplied by the host as a callback: `allreduce(user, device_ptr, n_doubles, cuda_stream)` must
+ * enqueue an in-place fp64 sum-allreduce over all ranks ordered after prior work of `cuda_stream` (ncclAllReduce on
+ * that stream, or torch.distributed as quantit_b200/sharding.py does) and return 0 on success. */
+typedef int (*qtb_allreduce_fn)(void *user, double *device_ptr, int64_t n, void *cuda_stream);
+qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce_fn allreduce, void *user);
+/* longest-processing-time-first assignment of n weighted sections to `world` ranks (pure host; deterministic: ties go
+ * to the lower section index / lower rank). owner_out[n]. */
+qtb_status qtb_lpt_assign(int64_t n, const double *weights, int world, int32_t *owner_out);
+
 /* ---- tensors: storage (replaces class btensor's block list, btensor.h:105-110,821-837) ---------------------- */
 /* Create from host data. `block_index` is [nblocks*rank] in any order (sorted internally); `host_data` holds the
  * blocks back to back in the GIVEN order, each C-contiguous with the dims implied by its sections; NULL = zeros.

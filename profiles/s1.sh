@@ -1,0 +1,10 @@
+set -u
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log
+for D in 1024 2048 4096; do
+  echo "== svd D=$D random"; QTB_SVD_DEBUG=1 timeout 300 python profiles/svd_driver.py 15 $D 1.6 2>&1 | tail -25
+done
+echo "== svd D=2048 decaying"; timeout 300 python profiles/svd_driver.py 15 2048 1.6 decay 2>&1 | tail -5
+echo "== dmrg L=100 maxbond 1024"
+QTB_PROFILE=1 timeout 900 python profiles/dmrg_sweep_bench.py 100 1024 1e-20 9 2>&1 | tail -30

@@ -415,6 +415,32 @@ qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncat
 	    });
 }
 
+qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce_fn allreduce, void *user)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx != nullptr, QTB_ERR_INVALID_ARGUMENT, "null context");
+		    QTB_REQUIRE(world >= 1 && rank >= 0 && rank < world, QTB_ERR_INVALID_ARGUMENT, "rank outside [0, world)");
+		    QTB_REQUIRE(world == 1 || allreduce != nullptr, QTB_ERR_INVALID_ARGUMENT,
+		                "sharding over more than one rank needs an allreduce callback");
+		    ctx->c.rank = rank;
+		    ctx->c.world = world;
+		    ctx->c.allreduce_fn = allreduce;
+		    ctx->c.allreduce_user = user;
+	    });
+}
+qtb_status qtb_lpt_assign(int64_t n, const double *weights, int world, int32_t *owner_out)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(n >= 0 && world >= 1 && (n == 0 || (weights && owner_out)), QTB_ERR_INVALID_ARGUMENT, "bad argument");
+		    const auto o = lpt_assign(std::vector<double>(weights, weights + n), world);
+		    std::copy(o.begin(), o.end(), owner_out);
+	    });
+}
+
 qtb_status qtb_heff_apply(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
                           const qtb_tensor *renv, qtb_tensor **out)
 {

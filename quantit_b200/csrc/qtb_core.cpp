@@ -2,6 +2,8 @@
 #include "qtb_core.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -119,10 +121,97 @@ Arena::~Arena()
 	}
 }
 
+static inline uint64_t mix64(uint64_t h, uint64_t v)
+{
+	h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+	h *= 0xff51afd7ed558ccdull;
+	h ^= h >> 33;
+	return h;
+}
+
 Plan::~Plan()
 {
 	if (d_blob && ctx)
 		cudaFreeAsync(d_blob, ctx->stream);
+	if (ctx)
+		for (auto &kv : owned)
+			if (kv.second.d_tiles)
+				cudaFreeAsync(kv.second.d_tiles, ctx->stream);
+}
+
+// =====================================================================================================================
+// charge-sector sharding
+// =====================================================================================================================
+void Ctx::allreduce(double *ptr, i64 n)
+{
+	if (world <= 1 || n <= 0)
+		return;
+	QTB_REQUIRE(allreduce_fn != nullptr, QTB_ERR_RUNTIME, "sharding is enabled but no allreduce callback is registered");
+	const int rc = allreduce_fn(allreduce_user, ptr, n, (void *)stream);
+	QTB_REQUIRE(rc == 0, QTB_ERR_RUNTIME, "the allreduce callback failed with code " + std::to_string(rc));
+	counters[0] += 1;
+}
+
+std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world)
+{ // longest processing time first: heaviest section to the least loaded rank; ties -> lower section / lower rank
+	const size_t n = weights.size();
+	std::vector<size_t> order(n);
+	std::iota(order.begin(), order.end(), size_t(0));
+	std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return weights[x] > weights[y]; });
+	std::vector<double> load(std::max(world, 1), 0.0);
+	std::vector<int32_t> owner(n, 0);
+	for (size_t s : order)
+	{
+		int best = 0;
+		for (int r = 1; r < (int)load.size(); ++r)
+			if (load[r] < load[best])
+				best = r;
+		owner[s] = best;
+		load[best] += weights[s];
+	}
+	return owner;
+}
+
+void add_section_weights(const Plan &plan, i64 owner_dim, std::vector<double> &weights)
+{
+	const Tensor &o = plan.out_proto;
+	QTB_REQUIRE(owner_dim >= 0 && owner_dim < o.st.rank, QTB_ERR_INVALID_ARGUMENT, "owner dim out of range");
+	if ((i64)weights.size() < o.st.nsec[owner_dim])
+		weights.resize(o.st.nsec[owner_dim], 0.0);
+	for (i64 b = 0; b < o.nblocks; ++b)
+		weights[o.idx(b)[owner_dim]] += (double)plan.out_flops[b] + 1.0; // +1: empty blocks still cost a tile visit
+}
+
+std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b,
+                                        i64 owner_dim, const std::vector<int32_t> &owner)
+{
+	uint64_t h = mix64(0x51a7d, (uint64_t)owner_dim * 131 + (uint64_t)ctx.rank * 7 + (uint64_t)ctx.world);
+	for (auto r : owner)
+		h = mix64(h, (uint64_t)r + 3);
+	auto it = plan->owned.find(h);
+	if (it == plan->owned.end())
+	{
+		const Tensor &o = plan->out_proto;
+		std::vector<GemmTile> mine;
+		Plan::Owned ow;
+		for (auto &t : plan->tiles)
+			if (owner[o.idx(t.out_blk)[owner_dim]] == ctx.rank)
+				mine.push_back(t);
+		for (i64 ob = 0; ob < o.nblocks; ++ob)
+			if (owner[o.idx(ob)[owner_dim]] == ctx.rank)
+				ow.flops += plan->out_flops[ob];
+		ow.ntiles = (int)mine.size();
+		if (!mine.empty())
+			ow.d_tiles = (GemmTile *)ctx_upload(ctx, mine.data(), mine.size() * sizeof(GemmTile));
+		it = plan->owned.emplace(h, ow).first;
+	}
+	auto out = std::make_unique<Tensor>(plan->out_proto);
+	out->arena = std::make_shared<Arena>(&ctx, plan->out_numel);
+	if (plan->out_numel)
+		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, plan->out_numel * sizeof(double), ctx.stream));
+	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr, out->arena->ptr,
+	                    &it->second);
+	return out;
 }
 
 // =====================================================================================================================
@@ -189,13 +278,6 @@ bool Tensor::packed_canonical() const
 		if (!block_contiguous(b))
 			return false;
 	return true;
-}
-static inline uint64_t mix64(uint64_t h, uint64_t v)
-{
-	h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
-	h *= 0xff51afd7ed558ccdull;
-	h ^= h >> 33;
-	return h;
 }
 void Tensor::compute_hash()
 {
@@ -774,6 +856,12 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 		go.pair_end = (int32_t)plan->pairs.size();
 		if (go.pair_end == go.pair_begin && M * N > 0)
 			need_zero = true;
+		{
+			i64 ksum = 0;
+			for (int p = go.pair_begin; p < go.pair_end; ++p)
+				ksum += plan->pairs[p].K;
+			plan->out_flops.push_back(2 * M * N * ksum);
+		}
 		plan->outs.push_back(go);
 		Ms.push_back(M);
 		Ns.push_back(N);
@@ -815,7 +903,24 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	(void)n64;
 	// 128x128 tiles when they fill the machine and do not waste much on block edges
 	plan->tile_cfg = (n128 >= ctx.sm_count && pad128 <= 1.25 * pad64) ? 1 : 0;
-	const int bm = plan->tile_cfg ? 128 : 64, bn = bm;
+	// skinny: every product is [M x K].[K x N] with K, N <= 16 (contraction with the MPO): CUDA-core row kernel
+	{
+		int max_n = 0, max_k = 0;
+		i64 max_m = 0;
+		for (auto &o : plan->outs)
+			if (o.pair_end > o.pair_begin)
+			{
+				max_n = std::max(max_n, (int)o.N);
+				max_m = std::max<i64>(max_m, o.M);
+			}
+		for (auto &pr : plan->pairs)
+			max_k = std::max(max_k, (int)pr.K);
+		plan->max_n = max_n;
+		if (max_n <= 16 && max_k <= 16 && max_m >= 64)
+			plan->tile_cfg = 2;
+	}
+	const int bm = plan->tile_cfg == 2 ? 512 : (plan->tile_cfg ? 128 : 64);
+	const int bn = plan->tile_cfg == 2 ? (1 << 30) : bm;
 	std::vector<std::pair<i64, GemmTile>> tl;
 	for (size_t ob = 0; ob < plan->outs.size(); ++ob)
 	{
@@ -879,10 +984,30 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 	return p;
 }
 
+void Ctx::prof_dump(const char *title)
+{
+	std::fprintf(stderr, "[qtb profile] %s\n", title);
+	for (auto &kv : prof)
+		std::fprintf(stderr, "[qtb profile]   %-28s calls %6ld built %5ld plan %9.2f ms gemm %9.2f ms  %8.3f GFLOP  %7.2f TFLOP/s tiles %ld\n",
+		             kv.first.c_str(), (long)kv.second.calls, (long)kv.second.built, kv.second.plan_ms, kv.second.gemm_ms,
+		             kv.second.flops * 1e-9, kv.second.gemm_ms > 0 ? kv.second.flops / kv.second.gemm_ms * 1e-9 : 0.0,
+		             (long)kv.second.tiles);
+	prof.clear();
+}
+
 std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
                                   const std::vector<i64> &dims_b)
 {
+	std::chrono::steady_clock::time_point t0, t1;
+	const i64 built0 = ctx.counters[2];
+	if (ctx.prof_level >= 2)
+	{
+		cudaStreamSynchronize(ctx.stream);
+		t0 = std::chrono::steady_clock::now();
+	}
 	auto plan = get_plan(ctx, a, b, dims_a, dims_b);
+	if (ctx.prof_level >= 2)
+		t1 = std::chrono::steady_clock::now();
 	auto out = std::make_unique<Tensor>(plan->out_proto);
 	out->arena = std::make_shared<Arena>(&ctx, plan->out_numel);
 	bool any_empty = false;
@@ -892,6 +1017,20 @@ std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, co
 		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, plan->out_numel * sizeof(double), ctx.stream));
 	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr,
 	                    out->arena->ptr);
+	if (ctx.prof_level >= 2)
+	{
+		cudaStreamSynchronize(ctx.stream);
+		auto t2 = std::chrono::steady_clock::now();
+		std::string key = "r" + std::to_string(a.st.rank) + "xr" + std::to_string(b.st.rank) + " k" + std::to_string(dims_a.size()) +
+		                  " a" + (dims_a.empty() ? std::string("-") : std::to_string(dims_a[0])) + " cfg" + std::to_string(plan->tile_cfg);
+		auto &r = ctx.prof[key];
+		r.calls += 1;
+		r.built += ctx.counters[2] - built0;
+		r.flops += plan->flops;
+		r.tiles += (i64)plan->tiles.size();
+		r.plan_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+		r.gemm_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+	}
 	return out;
 }
 

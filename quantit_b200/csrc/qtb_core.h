@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -183,7 +184,8 @@ struct Plan
 	std::vector<GemmTile> tiles; // sorted by decreasing cost
 	std::vector<int32_t> offpool;
 	i64 flops = 0;
-	int tile_cfg = 0; // 0: 64x64 tiles, 1: 128x128 tiles
+	int tile_cfg = 0; // 0: 64x64 tiles, 1: 128x128 tiles, 2: skinny (one thread per output row, N and K <= 16)
+	int max_n = 0;    // largest N over the output blocks
 	// device copies
 	void *d_blob = nullptr;
 	GemmOut *d_outs = nullptr;
@@ -192,6 +194,15 @@ struct Plan
 	int32_t *d_offpool = nullptr;
 	int *d_counter = nullptr;
 	Ctx *ctx = nullptr;
+	// charge-sector sharding: the tiles of the output blocks one rank owns, keyed by a hash of (owner dim, owner map, rank)
+	struct Owned
+	{
+		GemmTile *d_tiles = nullptr;
+		int ntiles = 0;
+		i64 flops = 0;
+	};
+	std::unordered_map<uint64_t, Owned> owned;
+	std::vector<i64> out_flops; // [out blocks] 2 M N sum K
 	~Plan();
 };
 
@@ -209,6 +220,20 @@ struct Ctx
 	void *pinned = nullptr;
 	size_t pinned_bytes = 0;
 	void *pinned_buf(size_t bytes);
+	// QTB_PROFILE=2 diagnostics: per contraction signature {calls, plan-build ms, kernel ms (synchronised), flops, tiles}
+	int prof_level = 0;
+	struct ProfRec
+	{
+		i64 calls = 0, flops = 0, tiles = 0, built = 0;
+		double plan_ms = 0, gemm_ms = 0;
+	};
+	std::map<std::string, ProfRec> prof;
+	void prof_dump(const char *title);
+	// charge-sector sharding (qtb_ctx_set_sharding)
+	int rank = 0, world = 1;
+	qtb_allreduce_fn allreduce_fn = nullptr;
+	void *allreduce_user = nullptr;
+	void allreduce(double *ptr, i64 n); // in-place sum over ranks, stream ordered; no-op when world == 1
 	~Ctx();
 };
 
@@ -227,7 +252,16 @@ void download(Ctx &ctx, const Tensor &t, double *host_out);
 std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t); // packed copy (gathers strided views)
 
 // kernels (qtb_gemm.cu / qtb_vec.cu)
-void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c);
+void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
+                         const Plan::Owned *owned = nullptr);
+// sharding helpers (qtb_core.cpp)
+std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world);
+// one step of a sharded chain of contractions: computes only the output blocks whose section along `owner_dim` belongs
+// to this rank (the rest of the freshly allocated arena is zero); `owner` maps sections of that dim to ranks.
+std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b,
+                                        i64 owner_dim, const std::vector<int32_t> &owner);
+// a chain of contractions sharing one owner leg: accumulates the planner's flops per section of that leg
+void add_section_weights(const Plan &plan, i64 owner_dim, std::vector<double> &weights);
 void launch_gather_blocks(Ctx &ctx, const Tensor &src, double *dst_packed, const std::vector<i64> &dst_offs);
 
 } // namespace qtb

@@ -94,6 +94,7 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 	n_sweeps = 0;
 	// QTB_PROFILE=1: per-phase wall time with a stream sync after every phase (diagnostics only, perturbs the timing)
 	const bool prof = std::getenv("QTB_PROFILE") != nullptr;
+	ctx.prof_level = prof ? std::atoi(std::getenv("QTB_PROFILE")) : 0;
 	double tph[5] = {0, 0, 0, 0, 0};
 	auto tick = [&](int ph, std::chrono::steady_clock::time_point &t)
 	{
@@ -112,7 +113,7 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 		{
 			// ---- dmrg_2sites_update::operator(), dmrg.cpp:163-206 ----
 			auto tp = std::chrono::steady_clock::now();
-			auto theta = tensordot(ctx, *mps[oc], *mps[oc + 1], {2}, {0});
+			auto theta = tensordot_sharded(ctx, *mps[oc], *mps[oc + 1], {2}, {0}, 0);
 			tick(0, tp);
 			auto theta2 = two_sites_update(ctx, *theta, *h2[oc], *env[oc - 1], *env[oc + 2], &E);
 			theta.reset();
@@ -153,6 +154,8 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 			std::fprintf(stderr, "[qtb profile] sweep %ld: theta %.1f ms, lanczos %.1f ms, svd %.1f ms, absorb+env %.1f ms; plans built %ld, cache hits %ld, launches %ld\n",
 			             (long)it, tph[0], tph[1], tph[2], tph[3], (long)ctx.counters[2], (long)ctx.counters[3], (long)ctx.counters[0]);
 			tph[0] = tph[1] = tph[2] = tph[3] = 0;
+			if (ctx.prof_level >= 2)
+				ctx.prof_dump("contractions of this sweep (synchronised per call)");
 		}
 		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
 		const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -22,6 +22,7 @@
 //    skipped at 8-row/8-column MMA granularity.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "qtb_core.h"
@@ -416,6 +417,62 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 	}
 }
 
+// ---- skinny contractions ------------------------------------------------------------------------------------------------
+// Step 2 of H_eff.psi and of the environment updates contracts the big intermediate with the MPO over (MPO bond,
+// physical legs): every matched pair is a [M x K].[K x N] product with M = D_a * D_b (10^4..10^6) and K, N <= the MPO
+// bond section size (1..3 for the models of the reference). That is a scaled sum of blocks, HBM bound: tiling it
+// 64x64 for the tensor cores wastes 60/64 of every tile and floods the planner with millions of tiles. Here one thread
+// owns one output row: it streams A(m, 0..K) of every pair (coalesced over m when the row stride is 1, which is the
+// case on the DMRG path), reads the tiny B through the read-only cache (the same address for the whole warp) and keeps
+// the N accumulators in registers. Work item = (output block, chunk of kSkinnyRows rows).
+constexpr int kSkinnyRows = 512;
+constexpr int kSkinnyN = 16; // max N (and max K per pair) the planner routes here
+
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles,
+                                                           const GemmOut *__restrict__ outs,
+                                                           const GemmPair *__restrict__ pairs,
+                                                           const int32_t *__restrict__ offpool,
+                                                           const double *__restrict__ A, const double *__restrict__ B,
+                                                           double *__restrict__ C)
+{
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+	{
+		const GemmTile tile = tiles[t];
+		const GemmOut ob = outs[tile.out_blk];
+		const int M = ob.M, N = ob.N;
+		const int mend = min(M, tile.m0 + kSkinnyRows);
+		for (int m = tile.m0 + threadIdx.x; m < mend; m += 256)
+		{
+			double acc[NMAX];
+#pragma unroll
+			for (int n = 0; n < NMAX; ++n)
+				acc[n] = 0.0;
+			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+			{
+				const GemmPair pr = pairs[p];
+				const bool a_aff = pr.a_rs >= 0, b_aff = pr.b_cs >= 0;
+				const double *Ar = A + pr.a_off + (a_aff ? (int64_t)m * pr.a_rs : (int64_t)offpool[pr.a_roff + m]);
+				const double *Bb = B + pr.b_off;
+				for (int k = 0; k < pr.K; ++k)
+				{
+					const double a = Ar[a_aff ? (int64_t)k * pr.a_ks : (int64_t)offpool[pr.a_koff + k]];
+					const double *Bk = Bb + (b_aff ? (int64_t)k * pr.b_ks : (int64_t)offpool[pr.b_koff + k]);
+#pragma unroll
+					for (int n = 0; n < NMAX; ++n)
+						if (n < N)
+							acc[n] += a * __ldg(Bk + (b_aff ? (int64_t)n * pr.b_cs : (int64_t)offpool[pr.b_coff + n]));
+				}
+			}
+			double *dst = C + ob.c_off + (size_t)m * N;
+#pragma unroll
+			for (int n = 0; n < NMAX; ++n)
+				if (n < N)
+					dst[n] = acc[n];
+		}
+	}
+}
+
 //                     BM   BN  BK  WM  WN  ST MINB realloc
 using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 4, 2, false>;   // 4 consumer warps + producer warpgroup = 256 threads
 using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + producer warpgroup = 384 threads
@@ -423,7 +480,8 @@ using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + 
 static int g_blocks_per_sm[2] = {0, 0};
 
 template <class Cfg>
-static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c)
+static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c,
+                       const GemmTile *d_tiles, int ntiles)
 {
 	auto kern = grouped_gemm_kernel<Cfg>;
 	if (g_blocks_per_sm[which] == 0)
@@ -433,26 +491,38 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 		QTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::kThreads, Cfg::kSmemBytes));
 		g_blocks_per_sm[which] = nb > 0 ? nb : 1;
 	}
-	const int ntiles = (int)plan.tiles.size();
 	int grid = ctx.sm_count * g_blocks_per_sm[which];
 	if (grid > ntiles)
 		grid = ntiles;
-	kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(plan.d_tiles, ntiles, plan.d_outs, plan.d_pairs,
+	kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs,
 	                                                            plan.d_offpool, a, b, c);
 	QTB_CUDA(cudaGetLastError());
 }
 
-void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c)
+void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
+                         const Plan::Owned *owned)
 {
-	if (plan.tiles.empty())
+	const GemmTile *d_tiles = owned ? owned->d_tiles : plan.d_tiles;
+	const int ntiles = owned ? owned->ntiles : (int)plan.tiles.size();
+	if (ntiles == 0)
 		return;
-	if (plan.tile_cfg == 0)
-		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c);
+	if (plan.tile_cfg == 2)
+	{
+		const int grid = std::min(ntiles, ctx.sm_count * 8);
+		if (plan.max_n <= 4)
+			skinny_gemm_kernel<4><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs, plan.d_offpool, a, b, c);
+		else
+			skinny_gemm_kernel<kSkinnyN><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs,
+			                                                            plan.d_offpool, a, b, c);
+		QTB_CUDA(cudaGetLastError());
+	}
+	else if (plan.tile_cfg == 0)
+		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c, d_tiles, ntiles);
 	else
-		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c);
+		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c, d_tiles, ntiles);
 	ctx.counters[0] += 1;
 	ctx.counters[1] += 1;
-	ctx.counters[6] += plan.flops;
+	ctx.counters[6] += owned ? owned->flops : plan.flops;
 }
 
 } // namespace qtb

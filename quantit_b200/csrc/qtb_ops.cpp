@@ -189,26 +189,81 @@ std::unique_ptr<Tensor> mul_lastdim(Ctx &ctx, const Tensor &a, const Tensor &d_i
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// A chain of three contractions that carries one free leg from the first operand to the result (the bra bond a' through
+// H_eff.psi, the new ket bond through an environment update). Single GPU: three grouped-GEMM launches. Sharded
+// (qtb_ctx_set_sharding, world > 1): the sections of that leg are balanced over the ranks with the planner's flop
+// counts of all three steps, every rank runs the three steps for its sections only — no exchange between the steps,
+// the leg's sector is preserved — and ONE allreduce of the (otherwise zero) result arena makes it whole on every rank.
+namespace
+{
+struct ChainStep
+{
+	std::vector<i64> da, db;
+	i64 owner_dim; // position of the carried leg in this step's output
+};
+std::unique_ptr<Tensor> run_chain(Ctx &ctx, const Tensor &first, const Tensor *const rhs[3], const ChainStep steps[3])
+{
+	if (ctx.world <= 1)
+	{
+		auto t1 = tensordot(ctx, first, *rhs[0], steps[0].da, steps[0].db);
+		auto t2 = tensordot(ctx, *t1, *rhs[1], steps[1].da, steps[1].db);
+		return tensordot(ctx, *t2, *rhs[2], steps[2].da, steps[2].db);
+	}
+	std::shared_ptr<Plan> plans[3];
+	plans[0] = get_plan(ctx, first, *rhs[0], steps[0].da, steps[0].db);
+	plans[1] = get_plan(ctx, plans[0]->out_proto, *rhs[1], steps[1].da, steps[1].db);
+	plans[2] = get_plan(ctx, plans[1]->out_proto, *rhs[2], steps[2].da, steps[2].db);
+	std::vector<double> w;
+	for (int i = 0; i < 3; ++i)
+		add_section_weights(*plans[i], steps[i].owner_dim, w);
+	const auto owner = lpt_assign(w, ctx.world);
+	auto t1 = tensordot_owned(ctx, plans[0], first, *rhs[0], steps[0].owner_dim, owner);
+	auto t2 = tensordot_owned(ctx, plans[1], *t1, *rhs[1], steps[1].owner_dim, owner);
+	t1.reset();
+	auto t3 = tensordot_owned(ctx, plans[2], *t2, *rhs[2], steps[2].owner_dim, owner);
+	t2.reset();
+	ctx.allreduce(t3->arena->ptr, t3->arena->numel);
+	return t3;
+}
+} // namespace
+
 std::unique_ptr<Tensor> heff_apply(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,
                                    const Tensor &renv)
-{ // reference hamil2site_times_state_impl, dmrg.cpp:520-531
-	auto t1 = tensordot(ctx, lenv, psi, {0}, {0});
-	auto t2 = tensordot(ctx, *t1, h2, {0, 2, 3}, {0, 4, 5});
-	return tensordot(ctx, *t2, renv, {1, 4}, {0, 1});
+{ // reference hamil2site_times_state_impl, dmrg.cpp:520-531. Carried leg: the bra bond a' of the left environment
+  // (t1 = [w,a',s1,s2,b], t2 = [a',b,s1',s2',w'], out = [a',s1',s2',b']).
+	const Tensor *rhs[3] = {&psi, &h2, &renv};
+	const ChainStep steps[3] = {{{0}, {0}, 1}, {{0, 2, 3}, {0, 4, 5}, 0}, {{1, 4}, {0, 1}, 0}};
+	return run_chain(ctx, lenv, rhs, steps);
 }
 std::unique_ptr<Tensor> env_left(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &lenv)
-{ // reference compute_left_env_impl, dmrg.cpp:424-459
-	auto t1 = tensordot(ctx, lenv, mps, {0}, {0});
-	auto t2 = tensordot(ctx, *t1, h, {0, 2}, {0, 3});
+{ // reference compute_left_env_impl, dmrg.cpp:424-459. Carried leg: the new ket bond b of the site tensor
+  // (t1 = [w,a',s,b], t2 = [a',b,s',w'], out = [b,w',b']).
 	auto mc = conj(mps);
-	return tensordot(ctx, *t2, *mc, {0, 2}, {0, 1});
+	const Tensor *rhs[3] = {&mps, &h, mc.get()};
+	const ChainStep steps[3] = {{{0}, {0}, 3}, {{0, 2}, {0, 3}, 1}, {{0, 2}, {0, 1}, 0}};
+	return run_chain(ctx, lenv, rhs, steps);
 }
 std::unique_ptr<Tensor> env_right(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &renv)
-{ // reference compute_right_env_impl, dmrg.cpp:468-493
-	auto t1 = tensordot(ctx, renv, mps, {0}, {2});
-	auto t2 = tensordot(ctx, *t1, h, {0, 3}, {2, 3});
+{ // reference compute_right_env_impl, dmrg.cpp:468-493. Carried leg: the new ket bond a of the site tensor
+  // (t1 = [w,b',a,s], t2 = [b',a,w',s'], out = [a,w',a']).
 	auto mc = conj(mps);
-	return tensordot(ctx, *t2, *mc, {3, 0}, {1, 2});
+	const Tensor *rhs[3] = {&mps, &h, mc.get()};
+	const ChainStep steps[3] = {{{0}, {2}, 2}, {{0, 3}, {2, 3}, 1}, {{3, 0}, {1, 2}, 0}};
+	return run_chain(ctx, renv, rhs, steps);
+}
+
+std::unique_ptr<Tensor> tensordot_sharded(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &da,
+                                          const std::vector<i64> &db, i64 owner_dim)
+{ // one contraction, output blocks sharded by the sections of output dim `owner_dim`, then made whole by an allreduce
+	if (ctx.world <= 1)
+		return tensordot(ctx, a, b, da, db);
+	auto plan = get_plan(ctx, a, b, da, db);
+	std::vector<double> w;
+	add_section_weights(*plan, owner_dim, w);
+	const auto owner = lpt_assign(w, ctx.world);
+	auto out = tensordot_owned(ctx, plan, a, b, owner_dim, owner);
+	ctx.allreduce(out->arena->ptr, out->arena->numel);
+	return out;
 }
 
 std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,

@@ -20,6 +20,8 @@ std::unique_ptr<Tensor> heff_apply(Ctx &ctx, const Tensor &psi, const Tensor &h2
                                    const Tensor &renv);
 std::unique_ptr<Tensor> env_left(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &lenv);
 std::unique_ptr<Tensor> env_right(Ctx &ctx, const Tensor &h, const Tensor &mps, const Tensor &renv);
+std::unique_ptr<Tensor> tensordot_sharded(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &da,
+                                          const std::vector<i64> &db, i64 owner_dim);
 std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tensor &h2, const Tensor &lenv,
                                          const Tensor &renv, double *energy);
 // qtb_svd.cu

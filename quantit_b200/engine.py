@@ -73,6 +73,8 @@ _SIGS = [
     ("qtb_ctx_sync", C.c_int, [vp]),
     ("qtb_ctx_stream", vp, [vp]),
     ("qtb_ctx_counters", C.c_int, [vp, p_i64]),
+    ("qtb_ctx_set_sharding", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("qtb_lpt_assign", C.c_int, [i64, p_f64, C.c_int, C.POINTER(C.c_int32)]),
     ("qtb_tensor_create", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64, C.POINTER(vp)]),
     ("qtb_tensor_adopt", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, C.POINTER(vp), p_i64,
                                    C.POINTER(vp)]),
@@ -108,6 +110,17 @@ _SIGS = [
     ("qtb_dmrg", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, p_f64, p_f64, p_i64]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def lpt_assign(weights: Sequence[float], world: int) -> List[int]:
+    """longest-processing-time-first assignment of weighted charge sectors to ranks (qtb_lpt_assign, pure host)"""
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1))
+    out = (C.c_int32 * max(len(w), 1))()
+    _check(load_library().qtb_lpt_assign(len(w), _pf(w), int(world), out))
+    return [int(out[i]) for i in range(len(w))]
 
 
 class DmrgOptionsC(C.Structure):
@@ -175,6 +188,29 @@ class Context:
         names = ["kernel_launches", "gemm_launches", "plans_built", "plan_cache_hits", "h2d_bytes", "d2h_bytes",
                  "gemm_flops", "device_bytes"]
         return dict(zip(names, [int(v) for v in out]))
+
+    def set_sharding(self, rank: int, world: int, allreduce=None) -> None:
+        """charge-sector sharding over `world` ranks (include/qtb.h, qtb_ctx_set_sharding). `allreduce(ptr, n, stream)`
+        must enqueue an in-place fp64 sum-allreduce of n doubles at device address ptr, ordered after the prior work
+        of CUDA stream `stream` (quantit_b200/sharding.py supplies the torch.distributed / NCCL one)."""
+        if allreduce is None:
+            self._ar_cb = None
+            _check(self.lib.qtb_ctx_set_sharding(self.h, int(rank), int(world), None, None))
+            self.rank, self.world = int(rank), int(world)
+            return
+
+        def _cb(user, ptr, n, stream):
+            try:
+                allreduce(int(ptr or 0), int(n), int(stream or 0))
+                return 0
+            except Exception:  # no exception may cross the C ABI
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._ar_cb = ALLREDUCE_FN(_cb)  # keep the trampoline alive as long as the context uses it
+        _check(self.lib.qtb_ctx_set_sharding(self.h, int(rank), int(world), C.cast(self._ar_cb, C.c_void_p), None))
+        self.rank, self.world = int(rank), int(world)
 
     def close(self) -> None:
         if getattr(self, "h", None):

@@ -87,6 +87,25 @@ def test_svd_larger_groups_and_splits(engine):
     check_svd(engine, orc.BT(**t2), 2, (1e-2, 1, 5, 2.0))
 
 
+@pytest.mark.parametrize("graded", [False, True])
+def test_svd_large_panel_path(engine, graded):
+    """groups of ~450 x 400: panels that do not fit in shared memory -> the tensor-core path (DMMA Gram / two-sided Jacobi
+    eig with descending eigenvalue order / DMMA update). Random blocks and DMRG-like graded blocks (singular values
+    spanning 40 orders of magnitude, numerically rank deficient)."""
+    rng = np.random.default_rng(5)
+    th = wl.rand_like(wl.shape([wl.bond(5, 700, 1.2, 2), wl.SPIN_HALF, wl.SPIN_HALF, wl.conj_leg(wl.bond(5, 620, 1.2, 2))],
+                               (0,)), rng)
+    if graded:
+        for k in th["blocks"]:
+            blk = th["blocks"][k]
+            u, s, vt = np.linalg.svd(blk.reshape(blk.shape[0], -1), full_matrices=False)
+            th["blocks"][k] = ((u * (s * np.exp(-0.4 * np.arange(len(s))))) @ vt).reshape(blk.shape)
+        check_svd(engine, orc.BT(**th), 2, (1e-10, 4, 300, 2.0))
+    else:
+        check_svd(engine, orc.BT(**th), 2, None)
+        check_svd(engine, orc.BT(**th), 2, (1e-3, 4, 500, 2.0))
+
+
 def test_heff_env_update_golden(engine):
     qb = engine
     psi, H2, L, R, W = (eng(qb, g("heff_" + n)) for n in ("psi", "H2", "L", "R", "W"))
