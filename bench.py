@@ -269,6 +269,70 @@ def time_e2e(torch, qb, ctx, w, steps, warmup):
     return float(np.mean(t)), int(ta.numel() + tb.numel()) * 8, int(numel.value) * 8
 
 
+
+def time_heff(torch, qb, ctx, n_sec, D, sigma, steps, warmup, flush_buf, dist=None):
+    """H_eff.psi = L.W.W.R.psi (details::hamil2site_times_state: three block contractions) on the T3 shapes of
+    SURVEY.md section 8d. With a sharded context (N > 1) this is ONE H_eff application split over all ranks by charge
+    sector of the bra bond + one allreduce (strong scaling)."""
+    from quantit_b200 import workloads as wl
+    psi, W, L, R = wl.heff_set(n_sec, D, sigma, seed=5)
+    bt = lambda d: qb.BTensor.from_host(**d, ctx=ctx)
+    Wb = bt(W)
+    H2 = Wb.tensordot(Wb, [2], [0]).permute([0, 1, 3, 4, 2, 5])
+    p, l, r = bt(psi), bt(L), bt(R)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(warmup):
+        qb.hamil2site_times_state(p, H2, l, r)
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    c1 = ctx.counters()
+    evs = []
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = qb.hamil2site_times_state(p, H2, l, r)
+            e1.record(stream)
+            evs.append((e0, e1))
+            del out
+    ctx.sync()
+    torch.cuda.synchronize()
+    c2 = ctx.counters()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    flops_rank = (c2["gemm_flops"] - c1["gemm_flops"]) / steps
+    if dist is not None:
+        t = torch.tensor([ms, flops_rank], dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, flops, max_share = float(tm[0].item()), float(t[1].item()), float(tm[1].item())
+    else:
+        flops, max_share = flops_rank, flops_rank
+    return {"ms_per_step": ms, "flops_per_step": int(flops), "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "largest_rank_share": max_share / flops if flops else None,
+            "launches_per_step": (c2["kernel_launches"] - c1["kernel_launches"]) / steps}
+
+
+def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20):
+    """two-site DMRG sweeps of the U(1) Heisenberg chain at a saturated bond dimension (BASELINE.json metric, first half:
+    "2-site DMRG sweep time"): inputs from quantit_b200.workloads (no reference code involved), exactly n_sweeps sweeps
+    (convergence_criterion = 0), wall seconds per sweep as the reference's dmrg_log_sweeptime records them."""
+    from quantit_b200 import workloads as wl
+    H = [qb.BTensor.from_host(**h, ctx=ctx) for h in wl.heisenberg_mpo(L)]
+    psi = [qb.BTensor.from_host(**p_, ctx=ctx) for p_ in wl.random_mps(L, 4, L % 2, seed=0)]
+    log = {}
+    c0 = ctx.counters()
+    E = qb.dmrg(H, psi, qb.dmrg_options(cutoff, 0.0, maxbond, 4, n_sweeps), oc=0, log=log)
+    c1 = ctx.counters()
+    return {"L": L, "maximum_bond": maxbond, "cutoff": cutoff, "energy": E, "sweep_seconds": log["seconds"],
+            "sweep_mid_bond": log["mid_bond"], "sweep_energy": log["energy"],
+            "updates_per_sweep": 2 * (L - 2), "gemm_flops_total": c1["gemm_flops"] - c0["gemm_flops"],
+            "kernel_launches_total": c1["kernel_launches"] - c0["kernel_launches"],
+            "seconds_last_sweep": log["seconds"][-1], "mid_bond_last_sweep": log["mid_bond"][-1]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="T1", choices=list(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the D=4096 side measurement and the CPU baseline")
+    ap.add_argument("--dmrg", default="64,256,7", help="L,maximum_bond,sweeps of the DMRG sweep-time side measurement "
+                    "('100,4096,8' is the BASELINE.json configs[2] run: minutes; '' skips it)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -316,6 +382,14 @@ def main():
     flops = w["info"]["flops"]
     value = world * flops / (ms * 1e-3) / 1e12
 
+    sharded = None
+    if dist is not None and not args.no_extra:
+        # strong scaling of ONE H_eff.psi at D=4096 over the ranks (charge-sector sharding + one NCCL allreduce)
+        from quantit_b200.sharding import enable_sharding
+        enable_sharding(ctx)
+        sharded = time_heff(torch, qb, ctx, 15, 4096, 1.6, 5, 3, flush_buf, dist)
+        ctx.set_sharding(0, 1, None)
+
     e2e_ms, h2d, d2h = time_e2e(torch, qb, ctx, w, max(3, min(args.steps, 10)), 2)
     if dist is not None:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -343,10 +417,21 @@ def main():
                                            "MEASURED_PEAKS.json has no fp64 entry; nominal B200 fp64 tensor peak 40 TFLOP/s",
                             }
         try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload]
+            line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            line["roofline"]["traffic_source"] = tr["source"]
+        except Exception:
+            pass
+        try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             line["roofline"]["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
         except Exception:
             pass
+        if sharded is not None:
+            sharded["roofline_frac_aggregate"] = sharded["value"] / (world * peak)
+            sharded["workload"] = ("ONE H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO) sharded over %d GPUs by "
+                                   "charge sector of the bra bond, one allreduce of the result; strong scaling" % world)
+            line["workloads"] = {"heff_D4096_sharded": sharded}
         if not args.no_extra and world == 1:
             extra = {}
             for name in ["T2"] if args.workload != "T2" else ["T1"]:
@@ -355,6 +440,13 @@ def main():
                 extra[name] = {"workload": WORKLOAD_DESC[name], "ms_per_step": sw["ms"], "value": ach, "unit": "TFLOP/s",
                                "flops_per_step": sw["info"]["flops"], "block_gemms": sw["info"]["pairs"],
                                "roofline_frac": ach / peak}
+            hf = time_heff(torch, qb, ctx, 15, 4096, 1.6, 5, 3, flush_buf, None)
+            hf["roofline_frac"] = hf["value"] / peak
+            hf["workload"] = "H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO): 3 block contractions"
+            extra["heff_D4096"] = hf
+            if args.dmrg:
+                Ld, Dd, nsw = (int(x) for x in args.dmrg.split(","))
+                extra["dmrg_sweep"] = time_dmrg_sweeps(qb, ctx, Ld, Dd, nsw)
             line["workloads"] = extra
             threads = os.cpu_count() or 1
             kind, cores, cms = reference_cpu_time(w["a"], w["b"], w["da"], w["db"], threads, 12)

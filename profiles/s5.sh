@@ -1,0 +1,6 @@
+set -u
+mkdir -p gpurun_out
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log
+echo "== dmrg L=100 maxbond 4096"
+QTB_PROFILE=2 timeout 1500 python profiles/dmrg_sweep_bench.py 100 4096 1e-20 7 2>&1 | tail -28

@@ -173,6 +173,8 @@ struct GemmPair
 	int32_t b_ks, b_cs;      // affine fast path: offset(k,n) = k*b_ks + n*b_cs   (b_cs < 0: use the tables)
 };
 
+constexpr int kSkinnyRows = 1024; // rows of an output block per work item of the skinny (MPO) contraction kernel
+
 struct Plan
 {
 	// output layout
@@ -181,7 +183,10 @@ struct Plan
 	// work
 	std::vector<GemmOut> outs;
 	std::vector<GemmPair> pairs;
-	std::vector<GemmTile> tiles; // sorted by decreasing cost
+	std::vector<GemmTile> tiles;     // grouped by CTA: CTA c runs tiles[cta_begin[c] .. cta_begin[c+1]), heaviest first
+	std::vector<int32_t> cta_begin;  // [ncta + 1]
+	std::vector<double> tile_cost;   // [tiles] modelled cycles (same order as tiles)
+	int ncta = 0;
 	std::vector<int32_t> offpool;
 	i64 flops = 0;
 	int tile_cfg = 0; // 0: 64x64 tiles, 1: 128x128 tiles, 2: skinny (one thread per output row, N and K <= 16)
@@ -191,14 +196,16 @@ struct Plan
 	GemmOut *d_outs = nullptr;
 	GemmPair *d_pairs = nullptr;
 	GemmTile *d_tiles = nullptr;
+	int32_t *d_cta_begin = nullptr;
 	int32_t *d_offpool = nullptr;
 	int *d_counter = nullptr;
 	Ctx *ctx = nullptr;
 	// charge-sector sharding: the tiles of the output blocks one rank owns, keyed by a hash of (owner dim, owner map, rank)
 	struct Owned
 	{
-		GemmTile *d_tiles = nullptr;
-		int ntiles = 0;
+		GemmTile *d_tiles = nullptr; // the tiles of this rank, grouped by CTA (then int32 cta_begin[ncta + 1])
+		int32_t *d_cta_begin = nullptr;
+		int ntiles = 0, ncta = 0;
 		i64 flops = 0;
 	};
 	std::unordered_map<uint64_t, Owned> owned;
@@ -216,6 +223,11 @@ struct Ctx
 	int sm_count = 148;
 	i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	std::unordered_map<uint64_t, std::shared_ptr<Plan>> plan_cache;
+	// caching device allocator (qtb_core.cpp: ctx_alloc / ctx_free)
+	std::map<size_t, std::vector<void *>> free_bins; // size class -> free blocks
+	std::unordered_map<void *, size_t> live_blocks;  // block -> size class
+	size_t cached_bytes = 0;
+	void trim_cache(); // returns every cached block to the driver (synchronises the stream)
 	// pinned staging for plan uploads / small downloads
 	void *pinned = nullptr;
 	size_t pinned_bytes = 0;
@@ -254,6 +266,10 @@ std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t); // packed copy (g
 // kernels (qtb_gemm.cu / qtb_vec.cu)
 void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
                          const Plan::Owned *owned = nullptr);
+// static tile schedule: longest-processing-time-first assignment of the cost-modelled tiles to `ncta` CTAs; reorders
+// `tiles`/`cost` so that the tiles of one CTA are contiguous (heaviest first) and returns cta_begin[ncta + 1]
+std::vector<int32_t> schedule_tiles(std::vector<GemmTile> &tiles, std::vector<double> &cost, int ncta);
+int gemm_grid_limit(const Ctx &ctx, int tile_cfg); // CTAs the grouped GEMM keeps resident (SM count x CTAs per SM)
 // sharding helpers (qtb_core.cpp)
 std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world);
 // one step of a sharded chain of contractions: computes only the output blocks whose section along `owner_dim` belongs

@@ -187,15 +187,10 @@ __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned sme
 	}
 }
 
-// snake order over the cost-sorted tile list: round r visits the CTAs forwards (even r) or backwards (odd r)
-__device__ __forceinline__ int tile_of(int round, int cta, int ncta)
-{
-	return round * ncta + ((round & 1) ? (ncta - 1 - cta) : cta);
-}
-
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
-    grouped_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles, const GemmOut *__restrict__ outs,
+    grouped_gemm_kernel(const GemmTile *__restrict__ tiles, const int32_t *__restrict__ cta_begin,
+                        const GemmOut *__restrict__ outs,
                         const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
                         const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C)
 {
@@ -219,7 +214,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 	}
 	__syncthreads();
 
-	const int ncta = gridDim.x, cta = blockIdx.x;
+	// static schedule from the planner: this CTA runs tiles [t_begin, t_end), heaviest first (LPT over modelled cycles)
+	const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
 
 	if (warp < 4)
 	{
@@ -229,13 +225,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		const int pt = tid; // 0..127
 		int stage = 0;
 		unsigned phase = 0;
-		for (int round = 0;; ++round)
+		for (int t = t_begin; t < t_end; ++t)
 		{
-			const int t = tile_of(round, cta, ncta);
-			if (round * ncta >= ntiles)
-				break;
-			if (t >= ntiles)
-				continue;
 			const GemmTile tile = tiles[t];
 			const GemmOut ob = outs[tile.out_blk];
 			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
@@ -284,13 +275,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		constexpr int NI = WN / 8;
 		int stage = 0;
 		unsigned phase = 0;
-		for (int round = 0;; ++round)
+		for (int t = t_begin; t < t_end; ++t)
 		{
-			const int t = tile_of(round, cta, ncta);
-			if (round * ncta >= ntiles)
-				break;
-			if (t >= ntiles)
-				continue;
 			const GemmTile tile = tiles[t];
 			const GemmOut ob = outs[tile.out_blk];
 			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
@@ -424,52 +410,88 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 // 64x64 for the tensor cores wastes 60/64 of every tile and floods the planner with millions of tiles. Here one thread
 // owns one output row: it streams A(m, 0..K) of every pair (coalesced over m when the row stride is 1, which is the
 // case on the DMRG path), reads the tiny B through the read-only cache (the same address for the whole warp) and keeps
-// the N accumulators in registers. Work item = (output block, chunk of kSkinnyRows rows).
-constexpr int kSkinnyRows = 512;
-constexpr int kSkinnyN = 16; // max N (and max K per pair) the planner routes here
+// the N accumulators in registers. Work item = (output block, chunk of kSkinnyRows rows); a thread owns kSkinnyR rows
+// 256 apart so that it has kSkinnyR independent loads in flight per pair; the pair descriptors of the block are staged
+// in shared memory once per work item.
+constexpr int kSkinnyR = kSkinnyRows / 256; // rows per thread: independent loads in flight
+constexpr int kSkinnyN = 16;                // max N (and max K per pair) the planner routes here
+constexpr int kSkinnyBatch = 32;            // pair descriptors staged in shared memory at a time
 
 template <int NMAX>
-__global__ void __launch_bounds__(256) skinny_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles,
+__global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles,
                                                            const GemmOut *__restrict__ outs,
                                                            const GemmPair *__restrict__ pairs,
                                                            const int32_t *__restrict__ offpool,
                                                            const double *__restrict__ A, const double *__restrict__ B,
                                                            double *__restrict__ C)
 {
+	constexpr int R = kSkinnyR;
+	__shared__ GemmPair sp[kSkinnyBatch];
+	static_assert(sizeof(GemmPair) % 4 == 0, "descriptor copied as words");
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
 		const GemmTile tile = tiles[t];
 		const GemmOut ob = outs[tile.out_blk];
 		const int M = ob.M, N = ob.N;
-		const int mend = min(M, tile.m0 + kSkinnyRows);
-		for (int m = tile.m0 + threadIdx.x; m < mend; m += 256)
+		int m[R];
+		bool ok[R];
+		double acc[R][NMAX];
+#pragma unroll
+		for (int i = 0; i < R; ++i)
 		{
-			double acc[NMAX];
+			m[i] = tile.m0 + i * 256 + threadIdx.x; // consecutive threads, consecutive rows: coalesced when the row stride is 1
+			ok[i] = m[i] < M;
 #pragma unroll
 			for (int n = 0; n < NMAX; ++n)
-				acc[n] = 0.0;
-			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+				acc[i][n] = 0.0;
+		}
+		for (int pb = ob.pair_begin; pb < ob.pair_end; pb += kSkinnyBatch)
+		{
+			const int np = min(kSkinnyBatch, ob.pair_end - pb);
+			__syncthreads();
+			for (int e = threadIdx.x; e < np * (int)(sizeof(GemmPair) / 4); e += 256)
+				reinterpret_cast<int32_t *>(sp)[e] = reinterpret_cast<const int32_t *>(pairs + pb)[e];
+			__syncthreads();
+			for (int p = 0; p < np; ++p)
 			{
-				const GemmPair pr = pairs[p];
+				const GemmPair &pr = sp[p];
 				const bool a_aff = pr.a_rs >= 0, b_aff = pr.b_cs >= 0;
-				const double *Ar = A + pr.a_off + (a_aff ? (int64_t)m * pr.a_rs : (int64_t)offpool[pr.a_roff + m]);
+				const double *Ab = A + pr.a_off;
 				const double *Bb = B + pr.b_off;
+				int64_t ro[R];
+#pragma unroll
+				for (int i = 0; i < R; ++i)
+					ro[i] = ok[i] ? (a_aff ? (int64_t)m[i] * pr.a_rs : (int64_t)offpool[pr.a_roff + m[i]]) : 0;
 				for (int k = 0; k < pr.K; ++k)
 				{
-					const double a = Ar[a_aff ? (int64_t)k * pr.a_ks : (int64_t)offpool[pr.a_koff + k]];
+					const int64_t ko = a_aff ? (int64_t)k * pr.a_ks : (int64_t)offpool[pr.a_koff + k];
+					double a[R];
+#pragma unroll
+					for (int i = 0; i < R; ++i)
+						a[i] = ok[i] ? Ab[ro[i] + ko] : 0.0;
 					const double *Bk = Bb + (b_aff ? (int64_t)k * pr.b_ks : (int64_t)offpool[pr.b_koff + k]);
 #pragma unroll
 					for (int n = 0; n < NMAX; ++n)
 						if (n < N)
-							acc[n] += a * __ldg(Bk + (b_aff ? (int64_t)n * pr.b_cs : (int64_t)offpool[pr.b_coff + n]));
+						{
+							const double bv = __ldg(Bk + (b_aff ? (int64_t)n * pr.b_cs : (int64_t)offpool[pr.b_coff + n]));
+#pragma unroll
+							for (int i = 0; i < R; ++i)
+								acc[i][n] += a[i] * bv;
+						}
 				}
 			}
-			double *dst = C + ob.c_off + (size_t)m * N;
-#pragma unroll
-			for (int n = 0; n < NMAX; ++n)
-				if (n < N)
-					dst[n] = acc[n];
 		}
+#pragma unroll
+		for (int i = 0; i < R; ++i)
+			if (ok[i])
+			{
+				double *dst = C + ob.c_off + (size_t)m[i] * N;
+#pragma unroll
+				for (int n = 0; n < NMAX; ++n)
+					if (n < N)
+						dst[n] = acc[i][n];
+			}
 	}
 }
 
@@ -481,7 +503,7 @@ static int g_blocks_per_sm[2] = {0, 0};
 
 template <class Cfg>
 static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c,
-                       const GemmTile *d_tiles, int ntiles)
+                       const GemmTile *d_tiles, const int32_t *d_cta_begin, int ncta)
 {
 	auto kern = grouped_gemm_kernel<Cfg>;
 	if (g_blocks_per_sm[which] == 0)
@@ -491,10 +513,7 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 		QTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::kThreads, Cfg::kSmemBytes));
 		g_blocks_per_sm[which] = nb > 0 ? nb : 1;
 	}
-	int grid = ctx.sm_count * g_blocks_per_sm[which];
-	if (grid > ntiles)
-		grid = ntiles;
-	kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs,
+	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_outs, plan.d_pairs,
 	                                                            plan.d_offpool, a, b, c);
 	QTB_CUDA(cudaGetLastError());
 }
@@ -503,7 +522,9 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
                          const Plan::Owned *owned)
 {
 	const GemmTile *d_tiles = owned ? owned->d_tiles : plan.d_tiles;
+	const int32_t *d_cta_begin = owned ? owned->d_cta_begin : plan.d_cta_begin;
 	const int ntiles = owned ? owned->ntiles : (int)plan.tiles.size();
+	const int ncta = owned ? owned->ncta : plan.ncta;
 	if (ntiles == 0)
 		return;
 	if (plan.tile_cfg == 2)
@@ -517,9 +538,9 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 		QTB_CUDA(cudaGetLastError());
 	}
 	else if (plan.tile_cfg == 0)
-		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c, d_tiles, ntiles);
+		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c, d_tiles, d_cta_begin, ncta);
 	else
-		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c, d_tiles, ntiles);
+		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c, d_tiles, d_cta_begin, ncta);
 	ctx.counters[0] += 1;
 	ctx.counters[1] += 1;
 	ctx.counters[6] += owned ? owned->flops : plan.flops;

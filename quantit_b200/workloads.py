@@ -143,3 +143,86 @@ def random_btensor(rng: np.random.Generator, rank: int, max_sec: int = 4, max_si
 
 def stored_bytes(desc) -> int:
     return int(sum(b.size for b in desc["blocks"].values())) * 8
+
+
+# ---- whole-chain inputs for the two-site DMRG workloads (BASELINE.json configs[0] and configs[2]) ---------------------
+def heisenberg_mpo(L: int, Jp: float = 0.25):
+    """U(1) Heisenberg S=1/2 open chain as a list of L rank-4 MPO site tensors W[wl, s', wr, s] (same operator as the
+    reference's Heisenberg(J=-1, L) after to_bMPO with the conserving bond charges, sources/models.cpp:24-70 and
+    SURVEY.md appendix C; not coalesced). Site 0 keeps only the last row of the bulk tensor (left bond = one section of
+    charge 0), site L-1 only the first column."""
+    bulk = heisenberg_W(Jp)
+    one = ([1], [(0,)])
+
+    def cut(left_row=None, right_col=None):
+        lb = one if left_row is not None else HEIS_MPO_BOND
+        rb = one if right_col is not None else HEIS_MPO_BOND
+        sh = shape([lb, SPIN_HALF, conj_leg(rb), conj_leg(SPIN_HALF)], (0,))
+        out = dict(sh)
+        out["blocks"] = {}
+        for (wl_, sp, wr, s), v in bulk["blocks"].items():
+            if left_row is not None and wl_ != left_row:
+                continue
+            if right_col is not None and wr != right_col:
+                continue
+            out["blocks"][(0 if left_row is not None else wl_, sp, 0 if right_col is not None else wr, s)] = v.copy()
+        return out
+
+    assert L >= 2
+    return [cut(left_row=4)] + [cut() for _ in range(L - 2)] + [cut(right_col=0)]
+
+
+def random_mps(L: int, bond: int, target: int, seed: int = 0):
+    """Random U(1) bMPS of total charge `target` (sum of the physical charges +-1), bond dimension <= `bond` spread over
+    the reachable charge sectors, right-orthonormal on sites 1..L-1 with the orthogonality centre on site 0 (what
+    quantit::random_bMPS + move_oc(0) hand to dmrg, sources/MPT.cpp). Site tensors A[l, s, r]: left leg charges q_l,
+    physical +-1, right leg -q_r with q_r = q_l + s; selection rule 0; the last right bond is one section of charge
+    `target`."""
+    rng = np.random.default_rng(seed)
+    assert (L + target) % 2 == 0 and abs(target) <= L
+    # bond k (between site k-1 and k): charges reachable from the left (k spins) and from the right (L-k spins)
+    bonds = []
+    for k in range(L + 1):
+        qs = [q for q in range(-k, k + 1, 2) if abs(target - q) <= L - k]
+        from math import comb
+        cap = [min(comb(k, (k + q) // 2), comb(L - k, (L - k + target - q) // 2)) for q in qs]
+        per = max(1, bond // max(1, len(qs)))
+        sizes = [int(min(c, per)) for c in cap]
+        bonds.append((sizes, [(q,) for q in qs]))
+    sites = []
+    for k in range(L):
+        sh = shape([bonds[k], SPIN_HALF, conj_leg(bonds[k + 1])], (0,))
+        t = rand_like(sh, rng)
+        for key in t["blocks"]:
+            t["blocks"][key] = t["blocks"][key] - 0.5
+        sites.append(t)
+    # right-orthonormalise from the right: per left sector, LQ of [D_l, (s, r)] and push L into the site on the left
+    for k in range(L - 1, 0, -1):
+        t = sites[k]
+        nl = len(t["sec_sizes"][0])
+        new_left = list(t["sec_sizes"][0])
+        lmats = {}
+        for ql in range(nl):
+            keys = sorted(key for key in t["blocks"] if key[0] == ql)
+            if not keys:
+                continue
+            M = np.concatenate([t["blocks"][key].reshape(t["blocks"][key].shape[0], -1) for key in keys], axis=1)
+            qmat, rmat = np.linalg.qr(M.T)  # M = rmat^T qmat^T
+            r = qmat.shape[1]
+            assert r == M.shape[0], "bond sector larger than what the right side can support"
+            lmats[ql] = rmat.T
+            pos = 0
+            for key in keys:
+                blk = t["blocks"][key]
+                w = blk.shape[1] * blk.shape[2]
+                t["blocks"][key] = np.ascontiguousarray(qmat.T[:, pos:pos + w]).reshape(blk.shape)
+                pos += w
+        left = sites[k - 1]
+        for key in list(left["blocks"]):
+            if key[2] in lmats:
+                left["blocks"][key] = np.ascontiguousarray(left["blocks"][key] @ lmats[key[2]])
+        t["sec_sizes"][0] = new_left
+    nrm = np.sqrt(sum(float((b * b).sum()) for b in sites[0]["blocks"].values()))
+    for key in sites[0]["blocks"]:
+        sites[0]["blocks"][key] = sites[0]["blocks"][key] / nrm
+    return sites

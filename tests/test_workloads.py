@@ -32,3 +32,22 @@ def test_qtbt_roundtrip(tmp_path):
     orc.write_qtbt(t, p)
     r = orc.read_qtbt(p)
     assert orc.same_structure(t, r) and orc.max_rel_err(t, r) == 0.0
+
+
+def test_chain_generators_feed_a_valid_dmrg():
+    """heisenberg_mpo + random_mps (the bench's DMRG inputs, generated without the reference): right-orthonormal MPS of
+    the requested charge, and the oracle's two-site DMRG on them finds the exact L=8 open-chain ground energy"""
+    import qtb_oracle as orc
+    L = 8
+    H = [orc.BT(**h) for h in wl.heisenberg_mpo(L)]
+    P = [orc.BT(**p) for p in wl.random_mps(L, 4, 0, seed=1)]
+    E = orc.dmrg(P, H, 0, 1e-12, 1e-12, 32, 4, 30)
+    assert abs(E - (-3.374932598687897)) < 1e-10
+    S = wl.random_mps(12, 16, 2, seed=3)
+    assert S[-1]["cvals"][2] == [(-2,)] and S[0]["cvals"][0] == [(0,)]
+    for k in range(1, 12):
+        t = S[k]
+        for ql in range(len(t["sec_sizes"][0])):
+            keys = sorted(key for key in t["blocks"] if key[0] == ql)
+            M = np.concatenate([t["blocks"][key].reshape(t["blocks"][key].shape[0], -1) for key in keys], axis=1)
+            assert np.allclose(M @ M.T, np.eye(M.shape[0]), atol=1e-12)
