@@ -14,7 +14,7 @@ if len(sys.argv) > 4:  # decaying spectrum like a real DMRG theta
         th["blocks"][k] = ((u * (s * np.exp(-0.15 * np.arange(len(s))))) @ vt).reshape(b.shape)
 T = qb.BTensor.from_host(**th)
 ctx = qb.default_context()
-for i in range(3):
+for i in range(int(os.environ.get("SVD_REPS", "3"))):
     ctx.sync(); t0 = time.perf_counter()
     U, d, V = qb.svd(T, 2, 1e-12, 4, D)
     ctx.sync(); print("svd ms", (time.perf_counter() - t0) * 1e3, "kept", sum(d.structure()[0][0]))

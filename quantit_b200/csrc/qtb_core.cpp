@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -219,14 +220,25 @@ std::vector<int32_t> schedule_tiles(std::vector<GemmTile> &tiles, std::vector<do
 	std::vector<size_t> order(n);
 	std::iota(order.begin(), order.end(), size_t(0));
 	std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return cost[x] > cost[y]; });
+	std::vector<std::vector<size_t>> per(ncta);
+	static const bool snake = std::getenv("QTB_SCHED") && std::string(std::getenv("QTB_SCHED")) == "snake";
+	if (snake)
+	{ // experiment switch: cost-sorted list dealt to the CTAs forwards, backwards, forwards, ...
+		for (size_t k = 0; k < n; ++k)
+		{
+			const size_t round = k / ncta, pos = k % ncta;
+			per[(round & 1) ? (ncta - 1 - pos) : pos].push_back(order[k]);
+		}
+	}
 	// min-heap of (load, cta)
 	using Slot = std::pair<double, int>;
 	std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> heap;
 	for (int c = 0; c < ncta; ++c)
 		heap.push({0.0, c});
-	std::vector<std::vector<size_t>> per(ncta);
 	for (size_t t : order)
 	{
+		if (snake)
+			break;
 		Slot s = heap.top();
 		heap.pop();
 		per[s.second].push_back(t);
@@ -739,11 +751,6 @@ bool unit_stride(const std::vector<int32_t> &o)
 			return false;
 	return true;
 }
-struct Cand
-{
-	std::vector<i64> key; // [freeA..., freeB..., contracted...]
-	i64 a, b;
-};
 } // namespace
 
 static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a_in,
@@ -821,40 +828,44 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	// ---- block-pair matching: reference two-pointer merge over "columns", btensor.cpp:2057-2108 ----
 	// Equivalent formulation: every (A block, B block) pair with equal contracted block indices, grouped by the output
 	// index (freeA, freeB) in ascending order, pairs inside a group in ascending contracted index.
-	std::map<std::vector<i64>, std::vector<i64>> b_by_contr;
+	// Keys are mixed-radix encodings of the block indices (radix = section count of the dim): their numeric order is the
+	// lexicographic order of the index vectors, and one sort of 128-bit integers replaces the map / vector compares.
+	using u128 = unsigned __int128;
+	for (i64 d = 0; d < ra; ++d)
+		QTB_REQUIRE(a.st.nsec[d] < (i64(1) << 15), QTB_ERR_INVALID_ARGUMENT, "more than 32767 sections along one dim");
+	for (i64 d = 0; d < rb; ++d)
+		QTB_REQUIRE(b.st.nsec[d] < (i64(1) << 15), QTB_ERR_INVALID_ARGUMENT, "more than 32767 sections along one dim");
+	auto encode = [](const Tensor &t, i64 blk, const std::vector<i64> &dl, u128 key)
+	{
+		for (auto d : dl)
+			key = key * (u128)std::max<i64>(t.st.nsec[d], 1) + (u128)t.idx(blk)[d];
+		return key;
+	};
+	std::vector<std::pair<u128, i64>> b_sorted(b.nblocks);
 	for (i64 j = 0; j < b.nblocks; ++j)
+		b_sorted[j] = {encode(b, j, dims_b, 0), j};
+	std::sort(b_sorted.begin(), b_sorted.end());
+	struct Cand
 	{
-		std::vector<i64> key(k);
-		for (i64 i = 0; i < k; ++i)
-			key[i] = b.idx(j)[dims_b[i]];
-		b_by_contr[key].push_back(j);
-	}
+		u128 okey, ckey;
+		i64 a, b;
+	};
 	std::vector<Cand> cands;
+	for (i64 i = 0; i < a.nblocks; ++i)
 	{
-		std::vector<i64> key(k);
-		for (i64 i = 0; i < a.nblocks; ++i)
-		{
-			for (i64 c = 0; c < k; ++c)
-				key[c] = a.idx(i)[dims_a[c]];
-			auto it = b_by_contr.find(key);
-			if (it == b_by_contr.end())
-				continue;
-			for (i64 j : it->second)
-			{
-				Cand cd;
-				cd.key.reserve(nfa + nfb + k);
-				for (auto d : free_a)
-					cd.key.push_back(a.idx(i)[d]);
-				for (auto d : free_b)
-					cd.key.push_back(b.idx(j)[d]);
-				cd.key.insert(cd.key.end(), key.begin(), key.end());
-				cd.a = i;
-				cd.b = j;
-				cands.push_back(std::move(cd));
-			}
-		}
+		// contracted key in B's radices (section counts of contracted dims agree, checked above)
+		u128 ck = 0;
+		for (i64 c = 0; c < k; ++c)
+			ck = ck * (u128)std::max<i64>(b.st.nsec[dims_b[c]], 1) + (u128)a.idx(i)[dims_a[c]];
+		auto lo = std::lower_bound(b_sorted.begin(), b_sorted.end(), std::make_pair(ck, (i64)-1));
+		if (lo == b_sorted.end() || lo->first != ck)
+			continue;
+		const u128 ka = encode(a, i, free_a, 0);
+		for (auto it = lo; it != b_sorted.end() && it->first == ck; ++it)
+			cands.push_back({encode(b, it->second, free_b, ka), ck, i, it->second});
 	}
-	std::sort(cands.begin(), cands.end(), [](const Cand &x, const Cand &y) { return x.key < y.key; });
+	std::sort(cands.begin(), cands.end(),
+	          [](const Cand &x, const Cand &y) { return x.okey != y.okey ? x.okey < y.okey : x.ckey < y.ckey; });
 
 	// ---- operand offset tables (the fused permute_bl, btensor.cpp:1843-1894) ----
 	struct OpTab
@@ -953,16 +964,18 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	};
 
 	// ---- group into output blocks ----
-	const i64 ro = out.st.rank;
 	bool need_zero = false;
 	size_t pos = 0;
 	std::vector<i64> Ms, Ns;
 	while (pos < cands.size())
 	{
 		size_t end = pos + 1;
-		while (end < cands.size() && std::equal(cands[pos].key.begin(), cands[pos].key.begin() + ro, cands[end].key.begin()))
+		while (end < cands.size() && cands[end].okey == cands[pos].okey)
 			++end;
-		out.index.insert(out.index.end(), cands[pos].key.begin(), cands[pos].key.begin() + ro);
+		for (auto d : free_a)
+			out.index.push_back(a.idx(cands[pos].a)[d]);
+		for (auto d : free_b)
+			out.index.push_back(b.idx(cands[pos].b)[d]);
 		GemmOut go{};
 		i64 M = 1, N = 1;
 		for (auto d : free_a)
@@ -1075,8 +1088,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	const int bm = plan->tile_cfg == 2 ? kSkinnyRows : (plan->tile_cfg ? 128 : 64);
 	const int bn = plan->tile_cfg == 2 ? (1 << 30) : bm;
 	// cost model of a tile (cycles of its busiest consumer warp): per K chunk a fixed part (barrier wait, fragment address
-	// set-up) + 16 cycles per DMMA.8x8x4 of the warp's valid 8x8 output atoms; plus the epilogue. Slivers at ragged block
-	// edges cost far less than full tiles: balancing on K alone left the SMs 18..51 % busy on configs[1] (ncu, round 1).
+	// set-up) + 16 cycles per DMMA.8x8x4 of a whole warp tile; plus the epilogue.
 	const int BKc = 16;
 	const int wm = plan->tile_cfg == 1 ? 64 : 32, wn = 32; // warp tile of the two tensor-core configurations
 	for (size_t ob = 0; ob < plan->outs.size(); ++ob)
@@ -1098,15 +1110,22 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 					c = 200.0 + (double)std::min<i64>(bm, o.M - m0) / 256.0 * (double)ksum * (4.0 + o.N);
 				else
 				{
-					const int am = (int)std::min<i64>(wm, o.M - m0 + 7) / 8, an = (int)std::min<i64>(wn, o.N - n0 + 7) / 8;
-					c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * std::max(1, am) * std::max(1, an));
+					// the busiest consumer warp of a tile always computes its whole warp tile (unpredicated path)
+					c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * (wm / 8) * (wn / 8));
 				}
-				plan->tiles.push_back(GemmTile{(int32_t)ob, m0, n0});
+				{
+					const GemmPair &p0 = plan->pairs[o.pair_begin];
+					plan->tiles.push_back(GemmTile{o.c_off, o.M, o.N, m0, n0, o.pair_begin, o.pair_end, (int32_t)ob, p0.K,
+					                               p0.a_kcontig | (p0.b_ncontig << 1), 0});
+				}
 				plan->tile_cost.push_back(c);
 			}
 	}
 	plan->ncta = std::max(1, std::min<int>((int)plan->tiles.size(), gemm_grid_limit(ctx, plan->tile_cfg)));
-	plan->cta_begin = schedule_tiles(plan->tiles, plan->tile_cost, plan->ncta);
+	if (plan->tile_cfg == 2) // the skinny kernel walks the list grid-stride: items are uniform, no static schedule needed
+		plan->cta_begin.assign(1, 0);
+	else
+		plan->cta_begin = schedule_tiles(plan->tiles, plan->tile_cost, plan->ncta);
 
 	// ---- upload ----
 	auto align = [](size_t x) { return (x + 255) & ~size_t(255); };

@@ -151,9 +151,16 @@ std::vector<i64> sort_blocks(i64 rank, std::vector<i64> &index);
 
 // ---- contraction plan ----------------------------------------------------------------------------------------------
 struct GemmTile
-{
-	int32_t out_blk; // which output block
-	int32_t m0, n0;  // tile origin inside the block matrix
+{ // one work item of the grouped GEMM: a tile of one output block, self-contained (the kernels fetch ONE descriptor per
+  // item, no dependent second fetch of the block's record)
+	i64 c_off;                    // element offset of the output block in the C arena
+	int32_t M, N;                 // matrix dims of the output block
+	int32_t m0, n0;               // tile origin inside the block matrix
+	int32_t pair_begin, pair_end; // matched pairs of the block (ascending contracted index)
+	int32_t out_blk;              // which output block (sharding filters on it)
+	int32_t K0, flags0;           // K and (a_kcontig | b_ncontig << 1) of the first pair: a single-pair block (every block of
+	                              // configs[1]) needs no pair-descriptor fetch on the consumer side at all
+	int32_t pad_;
 };
 struct GemmOut
 {

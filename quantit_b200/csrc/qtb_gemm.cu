@@ -190,7 +190,6 @@ __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned sme
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
     grouped_gemm_kernel(const GemmTile *__restrict__ tiles, const int32_t *__restrict__ cta_begin,
-                        const GemmOut *__restrict__ outs,
                         const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
                         const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C)
 {
@@ -225,14 +224,23 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		const int pt = tid; // 0..127
 		int stage = 0;
 		unsigned phase = 0;
+		// Descriptor look-ahead (ncu, configs[1]: the consumers spun 11 times per chunk on the full barrier because every
+		// tile cost the producer a tiles[] -> pairs[] -> operand chain of three dependent DRAM round trips while the ring
+		// only holds about one tile of chunks): the work item is fetched two tiles ahead and its first pair descriptor
+		// one tile ahead, so at a tile boundary the operand loads issue immediately.
+		const int t_last = t_end - 1;
+		GemmTile tile = tiles[t_begin < t_end ? t_begin : 0];
+		GemmTile next = tiles[t_begin + 1 <= t_last ? t_begin + 1 : (t_begin < t_end ? t_begin : 0)];
+		GemmPair pr0 = pairs[tile.pair_begin];
 		for (int t = t_begin; t < t_end; ++t)
 		{
-			const GemmTile tile = tiles[t];
-			const GemmOut ob = outs[tile.out_blk];
-			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
+			const GemmTile next2 = tiles[t + 2 <= t_last ? t + 2 : t];
+			const GemmPair pr0_next = pairs[next.pair_begin];
+			const GemmTile ob = tile;
+			const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
 			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
 			{
-				const GemmPair pr = pairs[p];
+				const GemmPair pr = (p == ob.pair_begin) ? pr0 : pairs[p];
 				const double *Ab = A + pr.a_off;
 				const double *Bb = B + pr.b_off;
 				const int32_t *aro = offpool + pr.a_roff;
@@ -257,6 +265,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					}
 				}
 			}
+			tile = next;
+			next = next2;
+			pr0 = pr0_next;
 		}
 		// drain: the async arrivals must have fired before the CTA (and its shared memory) goes away
 		asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -275,17 +286,22 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		constexpr int NI = WN / 8;
 		int stage = 0;
 		unsigned phase = 0;
+		// The consumers never wait on a descriptor at a tile boundary: the next work item is fetched while the current
+		// one computes and carries the first pair's K / layout flags; further pairs are fetched one pair ahead. (ncu,
+		// configs[1], first version: 4.7 long-scoreboard stall cycles per issued instruction from the dependent
+		// tiles[] -> outs[] -> pairs[] fetches.)
+		GemmTile tile = tiles[t_begin < t_end ? t_begin : 0];
 		for (int t = t_begin; t < t_end; ++t)
 		{
-			const GemmTile tile = tiles[t];
-			const GemmOut ob = outs[tile.out_blk];
-			const int M = ob.M, N = ob.N, m0 = tile.m0, n0 = tile.n0;
+			const GemmTile next = tiles[t + 1 < t_end ? t + 1 : t];
+			const GemmTile ob = tile;
+			tile = next;
+			const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
 			// number of 8-row / 8-column MMA groups of this warp that intersect the block
 			int mi_valid = (M - m0 - wm0 + 7) / 8;
 			mi_valid = mi_valid < 0 ? 0 : (mi_valid > MI ? MI : mi_valid);
 			int nj_valid = (N - n0 - wn0 + 7) / 8;
 			nj_valid = nj_valid < 0 ? 0 : (nj_valid > NI ? NI : nj_valid);
-			const bool full_tile = (mi_valid == MI) && (nj_valid == NI);
 			const bool any = (mi_valid > 0) && (nj_valid > 0);
 
 			double acc[MI][NI][2];
@@ -295,10 +311,16 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				for (int j = 0; j < NI; ++j)
 					acc[i][j][0] = acc[i][j][1] = 0.0;
 
+			int K = ob.K0, lay = ob.flags0;
 			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
 			{
-				const int K = pairs[p].K;
-				const int a_kc = pairs[p].a_kcontig, b_nc = pairs[p].b_ncontig;
+				int K_next = 0, lay_next = 0;
+				if (p + 1 < ob.pair_end)
+				{
+					K_next = pairs[p + 1].K;
+					lay_next = pairs[p + 1].a_kcontig | (pairs[p + 1].b_ncontig << 1);
+				}
+				const int a_kc = lay & 1, b_nc = lay >> 1;
 				const int sa_m = a_kc ? (BK + PAD) : 1;
 				const int sa_k = a_kc ? 1 : (BM + PAD);
 				const int sb_k = b_nc ? (BN + PAD) : 1;
@@ -311,7 +333,12 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					const double *Bs = As + Cfg::kASize;
 					const double *Ap = As + (wm0 + g) * sa_m + q * sa_k;
 					const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n;
-					if (full_tile)
+					// A warp whose 32-row x 32-column (64 x 32 for the large configuration) tile intersects the block
+					// computes ALL of it, unpredicated: rows / columns past the block edge were clamped by the producer
+					// (finite data, never stored) and the K tail is zero-filled. The first version skipped invalid 8x8
+					// atoms with per-atom predicates: 6.4 instructions per DMMA on configs[1] (ncu source view, 30 % of the
+					// consumer samples on integer / branch instructions) to save 1.49x -> 1.14x of padded DMMA work.
+					if (any)
 					{
 #pragma unroll
 						for (int kk = 0; kk < BK; kk += 4)
@@ -330,33 +357,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 									dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
 						}
 					}
-					else if (any)
-					{
-						const int kmax = (K - ch * BK) < BK ? (K - ch * BK) : BK;
-#pragma unroll
-						for (int kk = 0; kk < BK; kk += 4)
-						{
-							if (kk < kmax)
-							{
-								double af[MI], bf[NI];
-#pragma unroll
-								for (int i = 0; i < MI; ++i)
-									af[i] = (i < mi_valid) ? Ap[i * 8 * sa_m + kk * sa_k] : 0.0;
-#pragma unroll
-								for (int j = 0; j < NI; ++j)
-									bf[j] = (j < nj_valid) ? Bp[kk * sb_k + j * 8 * sb_n] : 0.0;
-#pragma unroll
-								for (int i = 0; i < MI; ++i)
-									if (i < mi_valid)
-									{
-#pragma unroll
-										for (int j = 0; j < NI; ++j)
-											if (j < nj_valid)
-												dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-									}
-							}
-						}
-					}
 					__syncwarp();
 					if (lane == 0)
 						mbar_arrive(empty0 + 8 * stage);
@@ -366,6 +366,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 						phase ^= 1;
 					}
 				}
+				K = K_next;
+				lay = lay_next;
 			}
 
 			// epilogue: the output block is a fresh packed row-major [M,N] matrix
@@ -419,7 +421,6 @@ constexpr int kSkinnyBatch = 32;            // pair descriptors staged in shared
 
 template <int NMAX>
 __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles,
-                                                           const GemmOut *__restrict__ outs,
                                                            const GemmPair *__restrict__ pairs,
                                                            const int32_t *__restrict__ offpool,
                                                            const double *__restrict__ A, const double *__restrict__ B,
@@ -430,8 +431,8 @@ __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(c
 	static_assert(sizeof(GemmPair) % 4 == 0, "descriptor copied as words");
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
 	{
-		const GemmTile tile = tiles[t];
-		const GemmOut ob = outs[tile.out_blk];
+		const GemmTile ob = tiles[t];
+		const GemmTile &tile = ob;
 		const int M = ob.M, N = ob.N;
 		int m[R];
 		bool ok[R];
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(c
 }
 
 //                     BM   BN  BK  WM  WN  ST MINB realloc
-using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 4, 2, false>;   // 4 consumer warps + producer warpgroup = 256 threads
+using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 5, 2, false>;   // 4 consumer warps + producer warpgroup = 256 threads
 using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + producer warpgroup = 384 threads
 
 static int g_blocks_per_sm[2] = {0, 0};
@@ -513,7 +514,7 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 		QTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::kThreads, Cfg::kSmemBytes));
 		g_blocks_per_sm[which] = nb > 0 ? nb : 1;
 	}
-	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_outs, plan.d_pairs,
+	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_pairs,
 	                                                            plan.d_offpool, a, b, c);
 	QTB_CUDA(cudaGetLastError());
 }
@@ -531,9 +532,9 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 	{
 		const int grid = std::min(ntiles, ctx.sm_count * 8);
 		if (plan.max_n <= 4)
-			skinny_gemm_kernel<4><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs, plan.d_offpool, a, b, c);
+			skinny_gemm_kernel<4><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_pairs, plan.d_offpool, a, b, c);
 		else
-			skinny_gemm_kernel<kSkinnyN><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_outs, plan.d_pairs,
+			skinny_gemm_kernel<kSkinnyN><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_pairs,
 			                                                            plan.d_offpool, a, b, c);
 		QTB_CUDA(cudaGetLastError());
 	}

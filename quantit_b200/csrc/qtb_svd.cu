@@ -202,6 +202,75 @@ __global__ void __launch_bounds__(256) svd_gram_mma_kernel(const SvdGroup *__res
 // must be accurate relative to the column norms, not to ||G||: tiny columns would never converge otherwise.
 // Also: the convergence gauge max |g_ij|/sqrt(g_ii g_jj) of the pair (folded into *offmax), and a skip flag for the
 // update kernel when the pair is already orthogonal to `skip_tol`.
+// 1/sqrt(x) to full double precision from the single-precision MUFU estimate + 2 Newton steps (the fp64 sqrt/div
+// sequences are the critical path of a rotation; the rotation stays orthogonal to rounding whatever t's accuracy is)
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+	double y = (double)rsqrtf((float)x);
+	y = y * (1.5 - 0.5 * x * y * y);
+	y = y * (1.5 - 0.5 * x * y * y);
+	return y;
+}
+
+// Jacobi rotation (cs, sn) that annihilates the off-diagonal element grc of the symmetric 2x2 [[grr, grc], [grc, gcc]]:
+// the small-angle solution t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (gcc - grr) / (2 grc), written without any
+// fp64 division or square root (each is a ~300-cycle dependent sequence, and this sits on the critical path of every
+// round of the in-shared-memory eigensolver): with d = gcc - grr, o = 2 grc, h = hypot(d, o):
+//   cs^2 = (1 + |d| / h) / 2,   sn = sign(d) o / (2 h cs)      (cs^2 + sn^2 = 1 identically)
+// d and o are first scaled by a power of two (exact) so that h^2 neither overflows nor underflows.
+__device__ __forceinline__ void jacobi_rotation_do(double d, double o, double &cs, double &sn, double &t)
+{
+	const double mx = fmax(fabs(d), fabs(o));
+	const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+	if (ex == 0 || ex >= 0x7fe)
+	{ // denormal / huge: the textbook formula
+		const double tau = d / o;
+		t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+		cs = 1.0 / sqrt(1.0 + t * t);
+		sn = t * cs;
+		return;
+	}
+	const double scale = __hiloint2double((2046 - ex) << 20, 0); // 2^(1023 - ex): max(|d|, |o|) lands in [1, 2)
+	d *= scale;
+	o *= scale;
+	const double rh = fast_rsqrt(d * d + o * o);
+	const double x = 0.5 + 0.5 * fabs(d) * rh;
+	const double rcs = fast_rsqrt(x);
+	cs = x * rcs;
+	sn = copysign(0.5, d) * o * rh * rcs;
+	t = sn * rcs;
+}
+
+// tan of the small-angle Jacobi rotation for (d, o) = (g_cc - g_rr, 2 g_rc), short dependent chain: the shared-memory
+// eigensolver is bound by the LATENCY of this computation (one per round, everything else waits on it), so the angle is
+// estimated in single precision — any t gives an exactly orthogonal rotation once cs = (1 + t^2)^-1/2 is formed in
+// double; an angle good to 1e-7 leaves 1e-7 of the off-diagonal element instead of 0, which the next sweep removes.
+// Tiny angles (|o| << |d|, every pair of a graded panel) would underflow single precision: t = o / (2 d) in double.
+__device__ __forceinline__ double jacobi_tan_fast(double d, double o)
+{
+	const double mx = fmax(fabs(d), fabs(o));
+	const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+	if (ex == 0 || ex >= 0x7fe)
+	{ // denormal / huge: the textbook formula
+		const double tau = d / o;
+		return (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+	}
+	const double scale = __hiloint2double((2046 - ex) << 20, 0); // exact power of two: max(|d|, |o|) lands in [1, 2)
+	d *= scale;
+	o *= scale;
+	if (fabs(o) < 2.44140625e-4 * fabs(d))
+	{ // t = o / (2 d) (1 - (o / 2d)^2 + ...): relative error < 2e-8
+		const float df = (float)d;
+		double y = (double)(1.0f / df);
+		y = y * (2.0 - d * y); // one Newton step: 1 / d to ~1e-14
+		return 0.5 * o * y;
+	}
+	const float df = (float)d, of = (float)o;
+	const float h = sqrtf(df * df + of * of);
+	const float tf = of / (fabsf(df) + h);
+	return (double)(df >= 0.0f ? tf : -tf);
+}
+
 constexpr int kEigThreads = 1024;
 constexpr int kLdE = kPMax + 1;
 constexpr size_t kEigSmem = 2 * kPMax * kLdE * sizeof(double);
@@ -210,7 +279,8 @@ __global__ void __launch_bounds__(kEigThreads) svd_eig_kernel(const SvdGroup *__
                                                                const SvdItem *__restrict__ items,
                                                                const double *__restrict__ gpart, int nch_max,
                                                                double *__restrict__ rot, int *__restrict__ flags,
-                                                               unsigned long long *offmax, double skip_tol, int inner_max)
+                                                               unsigned long long *offmax, double skip_tol, int inner_max,
+                                                               double inner_tol)
 {
 	extern __shared__ double eig_smem[];
 	double *sG = eig_smem, *sJ = eig_smem + kPMax * kLdE;
@@ -263,75 +333,144 @@ __global__ void __launch_bounds__(kEigThreads) svd_eig_kernel(const SvdGroup *__
 	if (!(gauge > skip_tol))
 		return;
 
+	// Inner iteration. Per tournament round (pe/2 disjoint index pairs):
+	//   A  32 threads (8 lanes of each of the first 4 warps, one per scheduler) compute the 32 rotations of the round, one
+	//      pair per thread — not one pair per warp with 32 redundant lanes: the fp64 SIMT pipe is the bottleneck of this
+	//      kernel (measured: 2700 cycles per round with redundant angles), every instruction saved counts 32-fold;
+	//   B  warp w applies rotation w to columns (r, c) of G and J;   C  ... and to rows (r, c) of G.
+	// The rotations are applied in their scaled ("fast Givens") form: with G = S G' S, J = J' S, S = diag(s), a rotation
+	// [[cs, sn], [-sn, cs]] in the (r, c) plane is  x_r' -= alpha x_c',  x_c' += beta x_r'  (alpha = t s_c / s_r,
+	// beta = t s_r / s_c, t = sn / cs) followed by s_r *= cs, s_c *= cs: two FMAs per element pair instead of two
+	// multiplies and two FMAs. s shrinks by at most 2^-1/2 per round, far from underflow over the <= 4 * 63 rounds here.
+	__shared__ double s_scale[kPMax], s_alpha[kPMax / 2], s_beta[kPMax / 2], s_csv[kPMax / 2];
+	__shared__ int s_pr[kPMax / 2], s_pc[kPMax / 2];
+	__shared__ unsigned long long s_gmax;
+	if (threadIdx.x < kPMax)
+		s_scale[threadIdx.x] = 1.0;
+	if (threadIdx.x == 0)
+		s_gmax = 0ull;
+	__syncthreads();
+	const int angle_pair = (warp < 4 && lane < 8) ? lane * 4 + warp : -1; // which pair of the round this thread solves
+	const double gauge2 = gauge * gauge;
 	for (int sweep = 0; sweep < inner_max; ++sweep)
 	{
 		int rotated = 0;
+		double gmax2 = 0.0; // largest (g_rc)^2 / (g_rr g_cc) met in this sweep (before the rotation)
 		for (int step = 0; step < pe - 1; ++step)
 		{
-			int r = 0, c = kPMax;
-			double cs = 1.0, sn = 0.0;
-			if (warp < pe / 2)
+			// ---- A: the rotations of this round ----
+			if (angle_pair >= 0 && angle_pair < pe / 2)
 			{ // tournament pairing: player pe-1 is fixed, the others rotate
 				int a, b;
-				if (warp == 0)
+				if (angle_pair == 0)
 				{
 					a = pe - 1;
 					b = step;
 				}
 				else
 				{
-					a = (step + warp) % (pe - 1);
-					b = (step - warp + (pe - 1)) % (pe - 1);
+					a = step + angle_pair; // both < pe - 1: one conditional subtraction replaces the modulo
+					a = a >= pe - 1 ? a - (pe - 1) : a;
+					b = step - angle_pair;
+					b = b < 0 ? b + (pe - 1) : b;
 				}
-				r = min(a, b);
-				c = max(a, b);
+				const int r = min(a, b), c = max(a, b);
+				double alpha = 0.0, beta = 0.0, cs = 1.0;
 				if (c < p)
 				{
 					const double grc = sG[r * kLdE + c], grr = sG[r * kLdE + r], gcc = sG[c * kLdE + c];
-					const double sc = sqrt(fabs(grr * gcc));
-					if (fabs(grc) > 1e-17 * sc && grc != 0.0)
+					const double sr = s_scale[r], sc = s_scale[c];
+					// 1 / s_r, 1 / s_c freshly (independent of the angle chain: no latency added), exactly consistent with s
+					double isr = fast_rsqrt(sr), isc = fast_rsqrt(sc);
+					isr *= isr;
+					isc *= isc;
+					const double sc2 = fabs(grr * gcc), g2 = grc * grc; // the scales cancel in g2 / sc2
+					if (g2 > 1e-34 * sc2 && grc != 0.0)
 					{
-						const double tau = (gcc - grr) / (2.0 * grc);
-						const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-						cs = 1.0 / sqrt(1.0 + t * t);
-						sn = t * cs;
-						if (fabs(grc) > 1e-15 * sc)
+						const double t = jacobi_tan_fast(sc * sc * gcc - sr * sr * grr, 2.0 * sr * sc * grc);
+						cs = fast_rsqrt(1.0 + t * t);
+						alpha = t * sc * isr;
+						beta = t * sr * isc;
+						if (g2 > 1e-30 * sc2)
 							rotated = 1;
+						if (sc2 > 0.0)
+							gmax2 = fmax(gmax2, g2 / sc2);
 					}
 				}
+				s_pr[angle_pair] = r;
+				s_pc[angle_pair] = (alpha != 0.0 || beta != 0.0) ? c : kPMax; // kPMax: nothing to do for this pair
+				s_alpha[angle_pair] = alpha;
+				s_beta[angle_pair] = beta;
+				s_csv[angle_pair] = cs;
 			}
-			const bool act = (c < p) && (sn != 0.0);
+			__syncthreads();
+			// ---- B: column rotations of G' and J' ----
+			const bool act = (warp < pe / 2) && (s_pc[warp] < kPMax);
+			int r = 0, c = 0;
+			double alpha = 0.0, beta = 0.0;
 			if (act)
-			{ // column rotations: G <- G R, J <- J R
+			{
+				r = s_pr[warp];
+				c = s_pc[warp];
+				alpha = s_alpha[warp];
+				beta = s_beta[warp];
 #pragma unroll
 				for (int h = 0; h < kPMax / 32; ++h)
 				{
 					const int i = lane + 32 * h;
 					const double gr = sG[i * kLdE + r], gc = sG[i * kLdE + c];
-					sG[i * kLdE + r] = cs * gr - sn * gc;
-					sG[i * kLdE + c] = sn * gr + cs * gc;
+					sG[i * kLdE + r] = gr - alpha * gc;
+					sG[i * kLdE + c] = gc + beta * gr;
 					const double jr = sJ[i * kLdE + r], jc = sJ[i * kLdE + c];
-					sJ[i * kLdE + r] = cs * jr - sn * jc;
-					sJ[i * kLdE + c] = sn * jr + cs * jc;
+					sJ[i * kLdE + r] = jr - alpha * jc;
+					sJ[i * kLdE + c] = jc + beta * jr;
 				}
 			}
 			__syncthreads();
+			// ---- C: row rotations of G', scale update ----
 			if (act)
-			{ // row rotations: G <- R^T G
+			{
 #pragma unroll
 				for (int h = 0; h < kPMax / 32; ++h)
 				{
 					const int j = lane + 32 * h;
 					const double gr = sG[r * kLdE + j], gc = sG[c * kLdE + j];
-					sG[r * kLdE + j] = cs * gr - sn * gc;
-					sG[c * kLdE + j] = sn * gr + cs * gc;
+					sG[r * kLdE + j] = gr - alpha * gc;
+					sG[c * kLdE + j] = gc + beta * gr;
+				}
+				if (lane == 0)
+				{
+					const double cs = s_csv[warp];
+					s_scale[r] *= cs;
+					s_scale[c] *= cs;
 				}
 			}
 			__syncthreads();
 		}
+		if (gmax2 > 0.0)
+			atomicMax(&s_gmax, (unsigned long long)__double_as_longlong(gmax2));
+		// fold the scales back (G <- S G' S, J <- J' S, s <- 1): keeps them O(1) whatever the number of sweeps
+		for (int e = threadIdx.x; e < kPMax * kPMax; e += kEigThreads)
+		{
+			const int i = e / kPMax, j = e % kPMax;
+			sG[i * kLdE + j] *= s_scale[i] * s_scale[j];
+			sJ[i * kLdE + j] *= s_scale[j];
+		}
+		__syncthreads();
+		if (threadIdx.x < kPMax)
+			s_scale[threadIdx.x] = 1.0;
 		if (!__syncthreads_or(rotated))
 			break;
+		// Off-diagonal elements left by a sweep that met relative size g are O(g^2). Once that is well below what this
+		// visit started from (the outer iteration is quadratically convergent itself) further inner sweeps buy nothing.
+		const double gm2 = __longlong_as_double((long long)s_gmax);
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_gmax = 0ull;
+		if (gm2 < 1e-2 && gm2 * gm2 < inner_tol * inner_tol * gauge2)
+			break;
 	}
+	__syncthreads();
 	// descending eigenvalue order
 	if (threadIdx.x < kPMax)
 	{
@@ -339,11 +478,11 @@ __global__ void __launch_bounds__(kEigThreads) svd_eig_kernel(const SvdGroup *__
 		int rank = k;
 		if (k < p)
 		{
-			const double dk = sG[k * kLdE + k];
+			const double dk = sG[k * kLdE + k] * s_scale[k] * s_scale[k];
 			rank = 0;
 			for (int j = 0; j < p; ++j)
 			{
-				const double dj = sG[j * kLdE + j];
+				const double dj = sG[j * kLdE + j] * s_scale[j] * s_scale[j];
 				rank += (dj > dk || (dj == dk && j < k)) ? 1 : 0;
 			}
 		}
@@ -354,7 +493,7 @@ __global__ void __launch_bounds__(kEigThreads) svd_eig_kernel(const SvdGroup *__
 	for (int e = threadIdx.x; e < kPMax * kPMax; e += kEigThreads)
 	{
 		const int i = e / kPMax, k = e % kPMax;
-		Jm[i * kPMax + s_rank[k]] = sJ[i * kLdE + k];
+		Jm[i * kPMax + s_rank[k]] = sJ[i * kLdE + k] * s_scale[k];
 	}
 }
 
@@ -456,16 +595,6 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPanelThreads = 1024; // 32 warps = one per disjoint pair of a 64-column round
 constexpr int kPanelInner = 3;      // at most this many inner sweeps per visit (stops as soon as a sweep rotates nothing)
-
-// 1/sqrt(x) to full double precision from the single-precision MUFU estimate + 2 Newton steps (the fp64 sqrt/div
-// sequences are the critical path of a rotation; the rotation stays orthogonal to rounding whatever t's accuracy is)
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-	double y = (double)rsqrtf((float)x);
-	y = y * (1.5 - 0.5 * x * y * y);
-	y = y * (1.5 - 0.5 * x * y * y);
-	return y;
-}
 
 __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup *__restrict__ groups,
                                                                    const SvdItem *__restrict__ items,
@@ -944,6 +1073,8 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				double *d_gpart = nullptr, *d_rot = nullptr;
 				int *d_flags = nullptr;
 				static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
+				// inner sweeps stop once the off-diagonal mass they leave (~ g^2) is below inner_tol x the pair's gauge
+				static const double inner_tol = std::getenv("QTB_SVD_INNER_TOL") ? std::atof(std::getenv("QTB_SVD_INNER_TOL")) : 1e-1;
 				if (!use_panel)
 				{
 					if (!big_attr_set)
@@ -977,7 +1108,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 						}
 						svd_gram_mma_kernel<<<dim3(nch_max, cnt), 256, 0, ctx.stream>>>(d_groups, its, X, d_gpart, nch_max);
 						svd_eig_kernel<<<cnt, kEigThreads, kEigSmem, ctx.stream>>>(d_groups, its, d_gpart, nch_max, d_rot, d_flags,
-						                                                        d_off + sweep, conv_tol, inner_max);
+						                                                        d_off + sweep, conv_tol, inner_max, inner_tol);
 						svd_update_mma_kernel<<<dim3((max_rows + kUpdRows - 1) / kUpdRows, cnt), 256, kUpdSmem, ctx.stream>>>(
 						    d_groups, its, X, d_rot, d_flags);
 						ctx.counters[0] += 3;
