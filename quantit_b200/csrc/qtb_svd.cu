@@ -46,7 +46,8 @@ struct SvdGroup
 	i64 x_off; // element offset of X_g = [A_g ; I] (column-major, ld = m + n) in the workspace
 	int m, n;  // A_g (after the optional transposition) is m x n with m >= n
 	int ld;
-	int nb;    // number of column blocks = ceil(n / kJB)
+	int nb;    // number of column blocks = ceil(n / jb)
+	int jb;    // column-block width of this call: kJB, or kJB / 2 when that lets the fused panel kernel hold the panels
 };
 struct SvdItem
 {
@@ -110,7 +111,7 @@ __global__ void identity_kernel(const SvdGroup *__restrict__ groups, int ngroups
 // Large-panel path (bond dimension beyond a few hundred): three kernels per round-robin step, the two O(m p^2) ones on
 // the fp64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA.8x8x4, the only fp64 MMA of sm_100a).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_width(const SvdGroup &G, int b) { return max(0, min(kJB, G.n - b * kJB)); }
+__device__ __forceinline__ int block_width(const SvdGroup &G, int b) { return max(0, min(G.jb, G.n - b * G.jb)); }
 
 __device__ __forceinline__ void svd_dmma(double &c0, double &c1, double a, double b)
 {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) svd_gram_mma_kernel(const SvdGroup *__res
 			double v = 0.0;
 			if (c < p && r < nr)
 			{
-				const int col = c < wi ? it.bi * kJB + c : it.bj * kJB + (c - wi);
+				const int col = c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi);
 				v = Xg[(i64)col * G.ld + r0 + r];
 			}
 			sP[c * kLdS + r] = v;
@@ -333,120 +334,171 @@ __global__ void __launch_bounds__(kEigThreads) svd_eig_kernel(const SvdGroup *__
 	if (!(gauge > skip_tol))
 		return;
 
-	// Inner iteration. Per tournament round (pe/2 disjoint index pairs):
-	//   A  32 threads (8 lanes of each of the first 4 warps, one per scheduler) compute the 32 rotations of the round, one
-	//      pair per thread — not one pair per warp with 32 redundant lanes: the fp64 SIMT pipe is the bottleneck of this
-	//      kernel (measured: 2700 cycles per round with redundant angles), every instruction saved counts 32-fold;
-	//   B  warp w applies rotation w to columns (r, c) of G and J;   C  ... and to rows (r, c) of G.
+	// Inner iteration. Per tournament round (pe/2 disjoint index pairs P = (x, y)):
+	//   A  32 threads (8 lanes of each of the first 4 warps, one per scheduler) compute the rotations of the round, one
+	//      pair per thread, short dependent chain (see jacobi_tan_fast);
+	//   B  warp w applies G <- T^T G T blockwise: lane q owns the 2x2 block G[P_w, P_q] and applies rotation w from the
+	//      left and rotation q from the right in registers — ONE pass over G per round instead of a column pass and a
+	//      row pass — then rotation w to columns (x, y) of J.
+	// The kernel is bound by shared-memory bandwidth (every round streams G and J through it: ncu / launch list, 290 us
+	// per call whatever the latency of phase A), so what counts is bytes per round: 2 x 32 KB (G) + 2 x 32 KB (J).
 	// The rotations are applied in their scaled ("fast Givens") form: with G = S G' S, J = J' S, S = diag(s), a rotation
-	// [[cs, sn], [-sn, cs]] in the (r, c) plane is  x_r' -= alpha x_c',  x_c' += beta x_r'  (alpha = t s_c / s_r,
-	// beta = t s_r / s_c, t = sn / cs) followed by s_r *= cs, s_c *= cs: two FMAs per element pair instead of two
-	// multiplies and two FMAs. s shrinks by at most 2^-1/2 per round, far from underflow over the <= 4 * 63 rounds here.
-	__shared__ double s_scale[kPMax], s_alpha[kPMax / 2], s_beta[kPMax / 2], s_csv[kPMax / 2];
-	__shared__ int s_pr[kPMax / 2], s_pc[kPMax / 2];
+	// [[cs, sn], [-sn, cs]] in the (x, y) plane is  v_x' -= alpha v_y',  v_y' += beta v_x'  (alpha = t s_y / s_x,
+	// beta = t s_x / s_y, t = sn / cs) followed by s_x *= cs, s_y *= cs: two FMAs per element pair instead of two
+	// multiplies and two FMAs. s shrinks by at most 2^-1/2 per round and is folded back after every sweep.
+	__shared__ double s_scale[kPMax], s_alpha[2][kPMax / 2], s_beta[2][kPMax / 2];
 	__shared__ unsigned long long s_gmax;
 	if (threadIdx.x < kPMax)
 		s_scale[threadIdx.x] = 1.0;
 	if (threadIdx.x == 0)
 		s_gmax = 0ull;
 	__syncthreads();
+	const int npair = pe / 2;
 	const int angle_pair = (warp < 4 && lane < 8) ? lane * 4 + warp : -1; // which pair of the round this thread solves
 	const double gauge2 = gauge * gauge;
 	for (int sweep = 0; sweep < inner_max; ++sweep)
 	{
 		int rotated = 0;
-		double gmax2 = 0.0; // largest (g_rc)^2 / (g_rr g_cc) met in this sweep (before the rotation)
+		double gmax2 = 0.0; // largest (g_xy)^2 / (g_xx g_yy) met in this sweep (before the rotation)
+		// J' <- J' T of round `rstep` for pair w (columns x, y of J over all rows): independent of G and of the scales, so it
+		// is deferred by one round and runs on warps 4..31 WHILE warps 0..3 solve the next round's rotations (phase A is a
+		// latency chain of ~1000 cycles during which the other 28 warps would otherwise sit at the barrier).
+		auto j_update = [&](int rstep, int w)
+		{
+			int x, y;
+			if (w == 0)
+			{
+				x = pe - 1;
+				y = rstep;
+			}
+			else
+			{
+				x = rstep + w;
+				x = x >= pe - 1 ? x - (pe - 1) : x;
+				y = rstep - w;
+				y = y < 0 ? y + (pe - 1) : y;
+			}
+			const double a = s_alpha[rstep & 1][w], b = s_beta[rstep & 1][w];
+			if (a != 0.0 || b != 0.0)
+			{
+#pragma unroll
+				for (int h = 0; h < kPMax / 32; ++h)
+				{
+					const int i = lane + 32 * h;
+					const double jx = sJ[i * kLdE + x], jy = sJ[i * kLdE + y];
+					sJ[i * kLdE + x] = jx - a * jy;
+					sJ[i * kLdE + y] = jy + b * jx;
+				}
+			}
+		};
+		int pending = -1; // round whose J update has not been applied yet
 		for (int step = 0; step < pe - 1; ++step)
 		{
+			if (warp >= 4 && pending >= 0)
+			{
+				const int v = warp - 4;
+				if (v < npair)
+					j_update(pending, v);
+				if (v + 28 < npair)
+					j_update(pending, v + 28);
+			}
 			// ---- A: the rotations of this round ----
-			if (angle_pair >= 0 && angle_pair < pe / 2)
-			{ // tournament pairing: player pe-1 is fixed, the others rotate
-				int a, b;
+			if (angle_pair >= 0 && angle_pair < npair)
+			{ // tournament pairing: player pe-1 is fixed, the others rotate. x and y are NOT ordered: lanes q = 1, 2, ...
+			  // get consecutive x (ascending) and y (descending), which keeps the block accesses of phase B conflict free
+				int x, y;
 				if (angle_pair == 0)
 				{
-					a = pe - 1;
-					b = step;
+					x = pe - 1;
+					y = step;
 				}
 				else
 				{
-					a = step + angle_pair; // both < pe - 1: one conditional subtraction replaces the modulo
-					a = a >= pe - 1 ? a - (pe - 1) : a;
-					b = step - angle_pair;
-					b = b < 0 ? b + (pe - 1) : b;
+					x = step + angle_pair; // both < pe - 1: one conditional subtraction replaces the modulo
+					x = x >= pe - 1 ? x - (pe - 1) : x;
+					y = step - angle_pair;
+					y = y < 0 ? y + (pe - 1) : y;
 				}
-				const int r = min(a, b), c = max(a, b);
-				double alpha = 0.0, beta = 0.0, cs = 1.0;
-				if (c < p)
+				double alpha = 0.0, beta = 0.0, cs = 1.0, sx = 1.0, sy = 1.0;
+				if (x < p && y < p)
 				{
-					const double grc = sG[r * kLdE + c], grr = sG[r * kLdE + r], gcc = sG[c * kLdE + c];
-					const double sr = s_scale[r], sc = s_scale[c];
-					// 1 / s_r, 1 / s_c freshly (independent of the angle chain: no latency added), exactly consistent with s
-					double isr = fast_rsqrt(sr), isc = fast_rsqrt(sc);
-					isr *= isr;
-					isc *= isc;
-					const double sc2 = fabs(grr * gcc), g2 = grc * grc; // the scales cancel in g2 / sc2
-					if (g2 > 1e-34 * sc2 && grc != 0.0)
+					const double gxy = sG[x * kLdE + y], gxx = sG[x * kLdE + x], gyy = sG[y * kLdE + y];
+					sx = s_scale[x];
+					sy = s_scale[y];
+					// 1 / s_x, 1 / s_y freshly (independent of the angle chain: no latency added), exactly consistent with s
+					double isx = fast_rsqrt(sx), isy = fast_rsqrt(sy);
+					isx *= isx;
+					isy *= isy;
+					const double sc2 = fabs(gxx * gyy), g2 = gxy * gxy; // the scales cancel in g2 / sc2
+					if (g2 > 1e-34 * sc2 && gxy != 0.0)
 					{
-						const double t = jacobi_tan_fast(sc * sc * gcc - sr * sr * grr, 2.0 * sr * sc * grc);
+						const double t = jacobi_tan_fast(sy * sy * gyy - sx * sx * gxx, 2.0 * sx * sy * gxy);
 						cs = fast_rsqrt(1.0 + t * t);
-						alpha = t * sc * isr;
-						beta = t * sr * isc;
+						alpha = t * sy * isx;
+						beta = t * sx * isy;
 						if (g2 > 1e-30 * sc2)
 							rotated = 1;
 						if (sc2 > 0.0)
 							gmax2 = fmax(gmax2, g2 / sc2);
 					}
 				}
-				s_pr[angle_pair] = r;
-				s_pc[angle_pair] = (alpha != 0.0 || beta != 0.0) ? c : kPMax; // kPMax: nothing to do for this pair
-				s_alpha[angle_pair] = alpha;
-				s_beta[angle_pair] = beta;
-				s_csv[angle_pair] = cs;
-			}
-			__syncthreads();
-			// ---- B: column rotations of G' and J' ----
-			const bool act = (warp < pe / 2) && (s_pc[warp] < kPMax);
-			int r = 0, c = 0;
-			double alpha = 0.0, beta = 0.0;
-			if (act)
-			{
-				r = s_pr[warp];
-				c = s_pc[warp];
-				alpha = s_alpha[warp];
-				beta = s_beta[warp];
-#pragma unroll
-				for (int h = 0; h < kPMax / 32; ++h)
-				{
-					const int i = lane + 32 * h;
-					const double gr = sG[i * kLdE + r], gc = sG[i * kLdE + c];
-					sG[i * kLdE + r] = gr - alpha * gc;
-					sG[i * kLdE + c] = gc + beta * gr;
-					const double jr = sJ[i * kLdE + r], jc = sJ[i * kLdE + c];
-					sJ[i * kLdE + r] = jr - alpha * jc;
-					sJ[i * kLdE + c] = jc + beta * jr;
+				s_alpha[step & 1][angle_pair] = alpha;
+				s_beta[step & 1][angle_pair] = beta;
+				if (cs != 1.0)
+				{ // nobody reads the scales before the next round's phase A (two barriers away)
+					s_scale[x] = sx * cs;
+					s_scale[y] = sy * cs;
 				}
 			}
 			__syncthreads();
-			// ---- C: row rotations of G', scale update ----
-			if (act)
+			// ---- B: G' <- T^T G' T by 2x2 blocks ----
+			if (warp < npair)
 			{
-#pragma unroll
-				for (int h = 0; h < kPMax / 32; ++h)
-				{
-					const int j = lane + 32 * h;
-					const double gr = sG[r * kLdE + j], gc = sG[c * kLdE + j];
-					sG[r * kLdE + j] = gr - alpha * gc;
-					sG[c * kLdE + j] = gc + beta * gr;
-				}
+				// lane q holds pair q of the round (same formula as phase A) and its rotation; the warp's own pair comes
+				// from lane `warp` by shuffle: two shared-memory loads per lane instead of ten
+				int xq, yq;
 				if (lane == 0)
 				{
-					const double cs = s_csv[warp];
-					s_scale[r] *= cs;
-					s_scale[c] *= cs;
+					xq = pe - 1;
+					yq = step;
+				}
+				else
+				{
+					xq = step + lane;
+					xq = xq >= pe - 1 ? xq - (pe - 1) : xq;
+					yq = step - lane;
+					yq = yq < 0 ? yq + (pe - 1) : yq;
+				}
+				double aQ = 0.0, bQ = 0.0;
+				if (lane < npair)
+				{
+					aQ = s_alpha[step & 1][lane];
+					bQ = s_beta[step & 1][lane];
+				}
+				const int x = __shfl_sync(0xffffffffu, xq, warp), y = __shfl_sync(0xffffffffu, yq, warp);
+				const double aP = __shfl_sync(0xffffffffu, aQ, warp), bP = __shfl_sync(0xffffffffu, bQ, warp);
+				const bool actP = (aP != 0.0) || (bP != 0.0);
+				if (lane < npair)
+				{
+					if (actP || aQ != 0.0 || bQ != 0.0)
+					{
+						const double g00 = sG[x * kLdE + xq], g01 = sG[x * kLdE + yq];
+						const double g10 = sG[y * kLdE + xq], g11 = sG[y * kLdE + yq];
+						const double h00 = g00 - aP * g10, h01 = g01 - aP * g11; // rows: T_P^T from the left
+						const double h10 = g10 + bP * g00, h11 = g11 + bP * g01;
+						sG[x * kLdE + xq] = h00 - aQ * h01; // columns: T_Q from the right
+						sG[x * kLdE + yq] = h01 + bQ * h00;
+						sG[y * kLdE + xq] = h10 - aQ * h11;
+						sG[y * kLdE + yq] = h11 + bQ * h10;
+					}
 				}
 			}
 			__syncthreads();
+			pending = step;
 		}
+		if (pending >= 0 && warp < npair) // the last round's J update (all warps are free here)
+			j_update(pending, warp);
+		__syncthreads();
 		if (gmax2 > 0.0)
 			atomicMax(&s_gmax, (unsigned long long)__double_as_longlong(gmax2));
 		// fold the scales back (G <- S G' S, J <- J' S, s <- 1): keeps them O(1) whatever the number of sweeps
@@ -531,7 +583,7 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 		double v = 0.0;
 		if (c < p && r < nr)
 		{
-			const int col = c < wi ? it.bi * kJB + c : it.bj * kJB + (c - wi);
+			const int col = c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi);
 			v = Xg[(i64)col * G.ld + r0 + r];
 		}
 		sA[c * kLdA + r] = v;
@@ -577,7 +629,7 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 					const int c = j * 8 + 2 * q + h;
 					if (c < p)
 					{
-						const int col = c < wi ? it.bi * kJB + c : it.bj * kJB + (c - wi);
+						const int col = c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi);
 						Xg[(i64)col * G.ld + r0 + r] = acc[i][j][h];
 					}
 				}
@@ -608,7 +660,7 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 	const int nrows = G.m + G.n;
 	const int ld = nrows | 1; // odd leading dimension: lanes walking a column never collide, columns are skewed
 	double *Xg = X + G.x_off;
-	auto gcol = [&](int c) { return c < wi ? it.bi * kJB + c : it.bj * kJB + (c - wi); };
+	auto gcol = [&](int c) { return c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi); };
 	for (int e = threadIdx.x; e < p * nrows; e += kPanelThreads)
 	{
 		const int c = e / nrows, r = e - c * nrows;
@@ -926,6 +978,17 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	std::vector<int> sig_off(ng);
 	i64 xtotal = 0, sig_total = 0;
 	int max_nb = 0;
+	// column-block width: the fused shared-memory panel kernel needs (m + n) x 2 jb doubles per panel. Up to 439 rows that
+	// fits with jb = 32; up to 879 rows with jb = 16 (bond dimensions up to ~900: the three-kernel tensor-core path costs
+	// >= 0.3 ms per round-robin step whatever the size, the panel kernel a few tens of microseconds).
+	i64 rows_max = 0;
+	for (i64 g = 0; g < ng; ++g)
+		rows_max = std::max(rows_max, groups[g].m + groups[g].n);
+	const size_t kPanelSmemMax = 220 * 1024;
+	int jb = kJB;
+	if ((size_t)(rows_max | 1) * 2 * kJB * sizeof(double) > kPanelSmemMax &&
+	    (size_t)(rows_max | 1) * kJB * sizeof(double) <= kPanelSmemMax)
+		jb = kJB / 2;
 	for (i64 g = 0; g < ng; ++g)
 	{
 		const i64 m = groups[g].transposed ? groups[g].n : groups[g].m;
@@ -935,7 +998,8 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		dg[g].m = (int)m;
 		dg[g].n = (int)n;
 		dg[g].ld = (int)(m + n);
-		dg[g].nb = (int)((n + kJB - 1) / kJB);
+		dg[g].jb = jb;
+		dg[g].nb = (int)((n + jb - 1) / jb);
 		max_nb = std::max(max_nb, dg[g].nb);
 		sig_off[g] = (int)sig_total;
 		sig_total += n;
@@ -1065,9 +1129,9 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					max_m = std::max(max_m, dg[g].m);
 				const double conv_tol = 1e-14 + 4.5e-16 * std::sqrt((double)max_m);
 				// panels that fit in shared memory take the fused Hestenes kernel
-				const size_t panel_smem = (size_t)((max_rows | 1)) * kPMax * sizeof(double);
+				const size_t panel_smem = (size_t)((max_rows | 1)) * 2 * jb * sizeof(double);
 				static bool panel_attr_set = false;
-				const bool use_panel = panel_smem <= 220 * 1024;
+				const bool use_panel = panel_smem <= kPanelSmemMax;
 				static bool big_attr_set = false;
 				const int nch_max = (max_m + kGramRows - 1) / kGramRows;
 				double *d_gpart = nullptr, *d_rot = nullptr;
