@@ -315,7 +315,28 @@ def time_heff(torch, qb, ctx, n_sec, D, sigma, steps, warmup, flush_buf, dist=No
             "launches_per_step": (c2["kernel_launches"] - c1["kernel_launches"]) / steps}
 
 
-def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20):
+def reference_dmrg_sweeps(L, maxbond, n_sweeps, cutoff, threads):
+    """per-sweep wall milliseconds of the compiled reference's own dmrg() on the host CPU (oracle/_ref/ref_harness heis:
+    its Heisenberg bMPO + its random bond-4 bMPS, same L / maximum_bond / cutoff, convergence_criterion 0). None when the
+    compiled reference is absent."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+    try:
+        out = subprocess.run([harness, "heis", str(L), str(maxbond), repr(cutoff), "0", str(n_sweeps), "0"],
+                             capture_output=True, text=True, timeout=900, env=env)
+    except subprocess.TimeoutExpired:
+        return None
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("SWEEP")]
+    if out.returncode != 0 or not rows:
+        return None
+    return {"sweep_seconds": [float(r[r.index("ms") + 1]) * 1e-3 for r in rows],
+            "sweep_mid_bond": [int(r[r.index("mid_bond") + 1]) for r in rows], "threads": threads,
+            "kind": "reference (oracle/_ref/ref_harness heis, the reference's own dmrg())"}
+
+
+def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20, with_reference=False):
     """two-site DMRG sweeps of the U(1) Heisenberg chain at a saturated bond dimension (BASELINE.json metric, first half:
     "2-site DMRG sweep time"): inputs from quantit_b200.workloads (no reference code involved), exactly n_sweeps sweeps
     (convergence_criterion = 0), wall seconds per sweep as the reference's dmrg_log_sweeptime records them."""
@@ -326,11 +347,20 @@ def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20):
     c0 = ctx.counters()
     E = qb.dmrg(H, psi, qb.dmrg_options(cutoff, 0.0, maxbond, 4, n_sweeps), oc=0, log=log)
     c1 = ctx.counters()
-    return {"L": L, "maximum_bond": maxbond, "cutoff": cutoff, "energy": E, "sweep_seconds": log["seconds"],
-            "sweep_mid_bond": log["mid_bond"], "sweep_energy": log["energy"],
-            "updates_per_sweep": 2 * (L - 2), "gemm_flops_total": c1["gemm_flops"] - c0["gemm_flops"],
-            "kernel_launches_total": c1["kernel_launches"] - c0["kernel_launches"],
-            "seconds_last_sweep": log["seconds"][-1], "mid_bond_last_sweep": log["mid_bond"][-1]}
+    out = {"workload": f"U(1) Heisenberg S=1/2 chain L={L}, two-site DMRG from a random bond-4 state, maximum_bond {maxbond}, "
+                       f"cutoff {cutoff:g}, exactly {n_sweeps} sweeps; the last sweep runs at the saturated bond dimension",
+           "L": L, "maximum_bond": maxbond, "cutoff": cutoff, "energy": E, "sweep_seconds": log["seconds"],
+           "sweep_mid_bond": log["mid_bond"], "sweep_energy": log["energy"],
+           "updates_per_sweep": 2 * (L - 2), "gemm_flops_total": c1["gemm_flops"] - c0["gemm_flops"],
+           "kernel_launches_total": c1["kernel_launches"] - c0["kernel_launches"],
+           "seconds_last_sweep": log["seconds"][-1], "mid_bond_last_sweep": log["mid_bond"][-1],
+           "unit": "s per sweep", "higher_is_better": False}
+    if with_reference:
+        ref = reference_dmrg_sweeps(L, maxbond, n_sweeps, cutoff, os.cpu_count() or 1)
+        if ref is not None:
+            ref["seconds_last_sweep"] = ref["sweep_seconds"][-1]
+            out["cpu_reference"] = ref
+    return out
 
 
 def main():
@@ -341,8 +371,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="T1", choices=list(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the D=4096 side measurement and the CPU baseline")
-    ap.add_argument("--dmrg", default="64,256,7", help="L,maximum_bond,sweeps of the DMRG sweep-time side measurement "
-                    "('100,4096,8' is the BASELINE.json configs[2] run: minutes; '' skips it)")
+    ap.add_argument("--dmrg", default="64,256,7;100,4096,7",
+                    help="';'-separated L,maximum_bond,sweeps of the DMRG sweep-time measurements ('100,4096,7' is the "
+                         "BASELINE.json configs[2] run, ~2.5 minutes; '' skips them). Runs with maximum_bond <= 512 also time "
+                         "the compiled reference's dmrg() on the host CPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -444,9 +476,13 @@ def main():
             hf["roofline_frac"] = hf["value"] / peak
             hf["workload"] = "H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO): 3 block contractions"
             extra["heff_D4096"] = hf
-            if args.dmrg:
-                Ld, Dd, nsw = (int(x) for x in args.dmrg.split(","))
-                extra["dmrg_sweep"] = time_dmrg_sweeps(qb, ctx, Ld, Dd, nsw)
+            for spec in [x for x in args.dmrg.split(";") if x.strip()]:
+                Ld, Dd, nsw = (int(x) for x in spec.split(","))
+                try:  # a side measurement must never cost the headline line
+                    extra[f"dmrg_sweep_L{Ld}_D{Dd}"] = time_dmrg_sweeps(qb, ctx, Ld, Dd, nsw, with_reference=(Dd <= 512))
+                except Exception as e:  # noqa: BLE001
+                    extra[f"dmrg_sweep_L{Ld}_D{Dd}"] = {"error": repr(e)[:300]}
+                ctx.trim_cache()
             line["workloads"] = extra
             threads = os.cpu_count() or 1
             kind, cores, cms = reference_cpu_time(w["a"], w["b"], w["da"], w["db"], threads, 12)

@@ -52,6 +52,9 @@ const char *qtb_version(void);
 qtb_status qtb_ctx_create(int device, void *stream, qtb_ctx **out);
 void qtb_ctx_destroy(qtb_ctx *ctx);
 qtb_status qtb_ctx_sync(qtb_ctx *ctx);
+/* returns the engine's cached (free) device blocks to the driver; live tensors are untouched. The reference has no
+ * counterpart (libtorch's CUDA caching allocator: c10::cuda::CUDACachingAllocator::emptyCache()). */
+qtb_status qtb_ctx_trim(qtb_ctx *ctx);
 void *qtb_ctx_stream(qtb_ctx *ctx);
 /* counters since context creation: [0] kernel launches of this library, [1] grouped-GEMM launches,
  * [2] plans built, [3] plan-cache hits, [4] bytes host->device, [5] bytes device->host,

@@ -137,6 +137,10 @@ qtb_status qtb_ctx_sync(qtb_ctx *ctx)
 {
 	return guarded([&]() { QTB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
 }
+qtb_status qtb_ctx_trim(qtb_ctx *ctx)
+{
+	return guarded([&]() { ctx->c.trim_cache(); });
+}
 void *qtb_ctx_stream(qtb_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
 qtb_status qtb_ctx_counters(qtb_ctx *ctx, int64_t out[8])
 {

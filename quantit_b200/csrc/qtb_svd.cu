@@ -680,18 +680,22 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 	{
 		for (int step = 0; step < pe - 1; ++step)
 		{
-			if (warp < pe / 2)
+			// pair pw of the round belongs to warp pw mod 32 (panels wider than 64 columns — whole small groups — give a
+			// warp two or more disjoint pairs per round)
+			for (int pw = warp; pw < pe / 2; pw += kPanelThreads / 32)
 			{
 				int a, b;
-				if (warp == 0)
+				if (pw == 0)
 				{
 					a = pe - 1;
 					b = step;
 				}
 				else
 				{
-					a = (step + warp) % (pe - 1);
-					b = (step - warp + (pe - 1)) % (pe - 1);
+					a = step + pw; // both < pe - 1: one conditional subtraction replaces the modulo
+					a = a >= pe - 1 ? a - (pe - 1) : a;
+					b = step - pw;
+					b = b < 0 ? b + (pe - 1) : b;
 				}
 				const int ci = min(a, b), cj = max(a, b);
 				if (cj < p)
@@ -722,10 +726,13 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 							worst = fmax(worst, fabs(ga) * fast_rsqrt(dd));
 						if (lane == 0)
 							s_rot = 1; // benign race: every writer stores 1
-						// angle in full double precision: on graded matrices (singular values spanning 1e-30 and more,
-						// every truncated DMRG theta) t underflows single precision and the sweep would never converge
-						const double zeta = (be - al) / (2.0 * ga);
-						const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+						// tan of the rotation with a short dependent chain (jacobi_tan_fast: single-precision estimate, double
+						// precision for the tiny angles of graded matrices — every truncated DMRG theta — which would
+						// underflow single precision); cs, sn in double: the rotation is orthogonal to rounding whatever
+						// t's accuracy is, and a 1e-7 error in t only leaves 1e-7 of the inner product for the next visit.
+						// The fp64 division + square roots of the textbook formula were ~1000 cycles on the critical path
+						// of each of the 63 rounds of a sweep.
+						const double t = jacobi_tan_fast(be - al, 2.0 * ga);
 						cs = fast_rsqrt(1.0 + t * t);
 						sn = cs * t;
 					}
@@ -986,8 +993,15 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		rows_max = std::max(rows_max, groups[g].m + groups[g].n);
 	const size_t kPanelSmemMax = 220 * 1024;
 	int jb = kJB;
-	if ((size_t)(rows_max | 1) * 2 * kJB * sizeof(double) > kPanelSmemMax &&
-	    (size_t)(rows_max | 1) * kJB * sizeof(double) <= kPanelSmemMax)
+	i64 cols_max = 0;
+	for (i64 g = 0; g < ng; ++g)
+		cols_max = std::max(cols_max, std::min(groups[g].m, groups[g].n));
+	const int jb_whole = (int)((cols_max + 1) / 2); // two column blocks per group: one panel = the whole matrix
+	if (jb_whole > kJB && (size_t)(rows_max | 1) * 2 * jb_whole * sizeof(double) <= kPanelSmemMax)
+		jb = jb_whole; // every group fits in ONE shared-memory panel: plain parallel one-sided Jacobi driven to convergence
+		               // inside one CTA per group (n - 1 rounds per sweep instead of 63 rounds x 3 per block-pair visit)
+	else if ((size_t)(rows_max | 1) * 2 * kJB * sizeof(double) > kPanelSmemMax &&
+	         (size_t)(rows_max | 1) * kJB * sizeof(double) <= kPanelSmemMax)
 		jb = kJB / 2;
 	for (i64 g = 0; g < ng; ++g)
 	{

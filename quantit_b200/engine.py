@@ -71,6 +71,7 @@ _SIGS = [
     ("qtb_ctx_create", C.c_int, [C.c_int, vp, C.POINTER(vp)]),
     ("qtb_ctx_destroy", None, [vp]),
     ("qtb_ctx_sync", C.c_int, [vp]),
+    ("qtb_ctx_trim", C.c_int, [vp]),
     ("qtb_ctx_stream", vp, [vp]),
     ("qtb_ctx_counters", C.c_int, [vp, p_i64]),
     ("qtb_ctx_set_sharding", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -177,6 +178,10 @@ class Context:
 
     def sync(self) -> None:
         _check(self.lib.qtb_ctx_sync(self.h))
+
+    def trim_cache(self) -> None:
+        """return the engine's cached free device blocks to the driver (qtb_ctx_trim)"""
+        _check(self.lib.qtb_ctx_trim(self.h))
 
     @property
     def stream(self) -> int:
