@@ -27,8 +27,37 @@ Ctx::~Ctx()
 	live_blocks.clear();
 	if (pinned)
 		cudaFreeHost(pinned);
+	if (pinned_gauge_)
+		cudaFreeHost(pinned_gauge_);
+	for (auto ev : aux_events)
+		cudaEventDestroy(ev);
+	for (auto st : aux_streams)
+		cudaStreamDestroy(st);
 	if (own_stream && stream)
 		cudaStreamDestroy(stream);
+}
+
+void Ctx::ensure_aux_streams(int n)
+{
+	while ((int)aux_streams.size() < n)
+	{
+		cudaStream_t st = nullptr;
+		QTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		aux_streams.push_back(st);
+	}
+	while (aux_events.size() < aux_streams.size() + 1)
+	{
+		cudaEvent_t ev = nullptr;
+		QTB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		aux_events.push_back(ev);
+	}
+}
+
+unsigned long long *Ctx::pinned_gauge()
+{
+	if (!pinned_gauge_)
+		QTB_CUDA(cudaMallocHost((void **)&pinned_gauge_, 64 * sizeof(unsigned long long)));
+	return pinned_gauge_;
 }
 
 void *Ctx::pinned_buf(size_t bytes)

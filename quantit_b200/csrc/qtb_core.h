@@ -235,6 +235,12 @@ struct Ctx
 	std::unordered_map<void *, size_t> live_blocks;  // block -> size class
 	size_t cached_bytes = 0;
 	void trim_cache(); // returns every cached block to the driver (synchronises the stream)
+	// auxiliary streams / events (block SVD lanes) and a small pinned read-back area; created on demand
+	std::vector<cudaStream_t> aux_streams;
+	std::vector<cudaEvent_t> aux_events; // [aux_streams.size() + 1]
+	unsigned long long *pinned_gauge_ = nullptr;
+	void ensure_aux_streams(int n);
+	unsigned long long *pinned_gauge(); // 64 pinned words
 	// pinned staging for plan uploads / small downloads
 	void *pinned = nullptr;
 	size_t pinned_bytes = 0;

@@ -646,11 +646,12 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 // three warp-reduced dot products of the columns themselves.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPanelThreads = 1024; // 32 warps = one per disjoint pair of a 64-column round
-constexpr int kPanelInner = 3;      // at most this many inner sweeps per visit (stops as soon as a sweep rotates nothing)
+constexpr int kPanelInner = 1;      // inner sweeps per visit (measured: 1 beats 2 and 3 by 20-45 % at bond dimension 512-768)
 
 __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup *__restrict__ groups,
                                                                    const SvdItem *__restrict__ items,
-                                                                   double *__restrict__ X, unsigned long long *offmax)
+                                                                   double *__restrict__ X, unsigned long long *offmax,
+                                                                   int panel_inner)
 {
 	extern __shared__ double sp[];
 	__shared__ int s_rot;
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 	const double rot_tol = 2.3e-16 * sqrt((double)G.m);
 	const double rot_tol2 = rot_tol * rot_tol;
 	// a panel that holds the whole matrix is driven to convergence here; otherwise a few inner sweeps per visit
-	const int max_inner = (G.nb <= 2) ? 30 : kPanelInner;
+	const int max_inner = (G.nb <= 2) ? 30 : panel_inner;
 	for (int sweep = 0; sweep < max_inner; ++sweep)
 	{
 		for (int step = 0; step < pe - 1; ++step)
@@ -1092,125 +1093,207 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			// successive sweeps pipelined. Row-cyclic order is what de Rijk's descending ordering needs: with the
 			// tournament (round-robin) order the sweep count on graded matrices grows linearly with the number of column
 			// blocks (47 sweeps at 64 blocks against 14 here, measured on a numpy model of this iteration).
-			int period_max = 1;
+			int max_rows_all = 0, max_m = 1;
 			for (i64 g = 0; g < ng; ++g)
-				period_max = std::max(period_max, dg[g].nb);
-			std::vector<SvdItem> items;
-			std::vector<int> step_begin(period_max + 1, 0);
-			for (int t = 0; t < period_max; ++t)
 			{
-				step_begin[t] = (int)items.size();
-				for (i64 g = 0; g < ng; ++g)
-				{
-					const int nb = dg[g].nb;
-					if (!mine(g))
-						continue;
-					if (nb == 1)
-					{
-						if (t == 0)
-							items.push_back({(int)g, 0, 0}); // a single block: rotate inside it
-						continue;
-					}
-					const int tau = t % nb;
-					for (int bi = 0; bi < nb; ++bi)
-					{
-						// bj = tau + 1 - bi (mod nb), keep bi < bj
-						int bj = ((tau + 1 - bi) % nb + nb) % nb;
-						if (bj > bi)
-							items.push_back({(int)g, bi, bj});
-					}
-				}
+				max_rows_all = std::max(max_rows_all, dg[g].ld);
+				max_m = std::max(max_m, dg[g].m);
 			}
-			step_begin[period_max] = (int)items.size();
-			// single-block groups use item (g,0,0): the panel is the block itself. block_width(bj) would double count,
-			// so encode bj = nb (an empty block) instead.
-			for (auto &it : items)
-				if (it.bi == it.bj)
-					it.bj = dg[it.group].nb; // width = min(kJB, n - nb*kJB) <= 0 -> clamp in kernels
-			int max_items = 0;
-			for (int t = 0; t < period_max; ++t)
-				max_items = std::max(max_items, step_begin[t + 1] - step_begin[t]);
-			if (max_items > 0)
+			const double conv_tol = 1e-14 + 4.5e-16 * std::sqrt((double)max_m);
+			// panels that fit in shared memory take the fused Hestenes kernel
+			const size_t panel_smem = (size_t)((max_rows_all | 1)) * 2 * jb * sizeof(double);
+			const bool use_panel = panel_smem <= kPanelSmemMax;
+			static bool panel_attr_set = false, big_attr_set = false;
+			static const int panel_inner = std::getenv("QTB_SVD_PANEL_INNER") ? std::atoi(std::getenv("QTB_SVD_PANEL_INNER")) : kPanelInner;
+			static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
+			// inner sweeps stop once the off-diagonal mass they leave (~ g^2) is below inner_tol x the pair's gauge
+			static const double inner_tol = std::getenv("QTB_SVD_INNER_TOL") ? std::atof(std::getenv("QTB_SVD_INNER_TOL")) : 1e-1;
+			static const int lanes_max = std::getenv("QTB_SVD_LANES") ? std::max(1, std::atoi(std::getenv("QTB_SVD_LANES"))) : 4;
+			if (!use_panel && !big_attr_set)
 			{
-				auto d_items = (SvdItem *)ctx_upload(ctx, items.data(), items.size() * sizeof(SvdItem));
-				unsigned long long *d_off = (unsigned long long *)ctx_alloc(ctx, kMaxSweeps * sizeof(unsigned long long));
-				QTB_CUDA(cudaMemsetAsync(d_off, 0, kMaxSweeps * sizeof(unsigned long long), ctx.stream));
-				int max_rows = 0;
-				for (i64 g = 0; g < ng; ++g)
-					max_rows = std::max(max_rows, dg[g].ld);
-				int max_m = 1;
-				for (i64 g = 0; g < ng; ++g)
-					max_m = std::max(max_m, dg[g].m);
-				const double conv_tol = 1e-14 + 4.5e-16 * std::sqrt((double)max_m);
-				// panels that fit in shared memory take the fused Hestenes kernel
-				const size_t panel_smem = (size_t)((max_rows | 1)) * 2 * jb * sizeof(double);
-				static bool panel_attr_set = false;
-				const bool use_panel = panel_smem <= kPanelSmemMax;
-				static bool big_attr_set = false;
-				const int nch_max = (max_m + kGramRows - 1) / kGramRows;
+				QTB_CUDA(cudaFuncSetAttribute(svd_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEigSmem));
+				QTB_CUDA(cudaFuncSetAttribute(svd_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdSmem));
+				big_attr_set = true;
+			}
+			if (use_panel && !panel_attr_set)
+			{
+				QTB_CUDA(cudaFuncSetAttribute(svd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+				panel_attr_set = true;
+			}
+			// Lanes: the charge groups are independent factorisations. On the tensor-core path every round-robin step is
+			// gram -> eig -> update with the eigensolver a ~0.27 ms latency-bound kernel that leaves the tensor cores idle,
+			// so the groups are dealt to a few lanes (LPT over their work), each lane runs its own step sequence on its own
+			// CUDA stream, and one lane's Gram / update GEMMs fill the machine while the others sit in their eigensolvers.
+			struct Lane
+			{
+				std::vector<i64> groups;
+				std::vector<SvdItem> items;
+				std::vector<int> step_begin;
+				int period = 1, max_items = 0, max_rows = 0, nch_max = 1;
+				SvdItem *d_items = nullptr;
+				unsigned long long *d_off = nullptr;
 				double *d_gpart = nullptr, *d_rot = nullptr;
 				int *d_flags = nullptr;
-				static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
-				// inner sweeps stop once the off-diagonal mass they leave (~ g^2) is below inner_tol x the pair's gauge
-				static const double inner_tol = std::getenv("QTB_SVD_INNER_TOL") ? std::atof(std::getenv("QTB_SVD_INNER_TOL")) : 1e-1;
+				cudaStream_t stream = nullptr;
+				bool active = true;
+				double load = 0.0;
+			};
+			std::vector<i64> my_groups;
+			for (i64 g = 0; g < ng; ++g)
+				if (mine(g))
+					my_groups.push_back(g);
+			const int nlanes = use_panel ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, my_groups.size()));
+			std::vector<Lane> lanes(nlanes);
+			{
+				std::vector<i64> order = my_groups;
+				auto weight = [&](i64 g) { return (double)dg[g].nb * dg[g].nb * (double)dg[g].ld + 1.0; };
+				std::stable_sort(order.begin(), order.end(), [&](i64 x, i64 y) { return weight(x) > weight(y); });
+				for (i64 g : order)
+				{
+					int best = 0;
+					for (int l = 1; l < nlanes; ++l)
+						if (lanes[l].load < lanes[best].load)
+							best = l;
+					lanes[best].groups.push_back(g);
+					lanes[best].load += weight(g);
+				}
+			}
+			ctx.ensure_aux_streams(nlanes - 1);
+			for (int l = 0; l < nlanes; ++l)
+			{
+				Lane &L = lanes[l];
+				L.stream = l == 0 ? ctx.stream : ctx.aux_streams[l - 1];
+				std::sort(L.groups.begin(), L.groups.end());
+				int max_m_l = 1;
+				for (i64 g : L.groups)
+				{
+					L.period = std::max(L.period, dg[g].nb);
+					L.max_rows = std::max(L.max_rows, dg[g].ld);
+					max_m_l = std::max(max_m_l, dg[g].m);
+				}
+				L.nch_max = (max_m_l + kGramRows - 1) / kGramRows;
+				L.step_begin.assign(L.period + 1, 0);
+				for (int t = 0; t < L.period; ++t)
+				{
+					L.step_begin[t] = (int)L.items.size();
+					for (i64 g : L.groups)
+					{
+						const int nb = dg[g].nb;
+						if (nb == 1)
+						{
+							if (t == 0)
+								L.items.push_back({(int)g, 0, 0}); // a single block: rotate inside it
+							continue;
+						}
+						const int tau = t % nb;
+						for (int bi = 0; bi < nb; ++bi)
+						{
+							// bj = tau + 1 - bi (mod nb), keep bi < bj
+							int bj = ((tau + 1 - bi) % nb + nb) % nb;
+							if (bj > bi)
+								L.items.push_back({(int)g, bi, bj});
+						}
+					}
+				}
+				L.step_begin[L.period] = (int)L.items.size();
+				// single-block groups use item (g,0,0): the panel is the block itself. block_width(bj) would double count,
+				// so encode bj = nb (an empty block) instead.
+				for (auto &it : L.items)
+					if (it.bi == it.bj)
+						it.bj = dg[it.group].nb; // width = min(jb, n - nb*jb) <= 0 -> clamp in kernels
+				for (int t = 0; t < L.period; ++t)
+					L.max_items = std::max(L.max_items, L.step_begin[t + 1] - L.step_begin[t]);
+				if (L.max_items == 0)
+				{
+					L.active = false;
+					continue;
+				}
+				L.d_items = (SvdItem *)ctx_upload(ctx, L.items.data(), L.items.size() * sizeof(SvdItem));
+				L.d_off = (unsigned long long *)ctx_alloc(ctx, kMaxSweeps * sizeof(unsigned long long));
+				QTB_CUDA(cudaMemsetAsync(L.d_off, 0, kMaxSweeps * sizeof(unsigned long long), ctx.stream));
 				if (!use_panel)
 				{
-					if (!big_attr_set)
-					{
-						QTB_CUDA(cudaFuncSetAttribute(svd_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEigSmem));
-						QTB_CUDA(cudaFuncSetAttribute(svd_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdSmem));
-						big_attr_set = true;
-					}
-					d_gpart = (double *)ctx_alloc(ctx, (size_t)max_items * nch_max * kPMax * kPMax * sizeof(double));
-					d_rot = (double *)ctx_alloc(ctx, (size_t)max_items * kPMax * kPMax * sizeof(double));
-					d_flags = (int *)ctx_alloc(ctx, (size_t)max_items * sizeof(int));
+					L.d_gpart = (double *)ctx_alloc(ctx, (size_t)L.max_items * L.nch_max * kPMax * kPMax * sizeof(double));
+					L.d_rot = (double *)ctx_alloc(ctx, (size_t)L.max_items * kPMax * kPMax * sizeof(double));
+					L.d_flags = (int *)ctx_alloc(ctx, (size_t)L.max_items * sizeof(int));
 				}
-				if (use_panel && !panel_attr_set)
+			}
+			// fork: the lanes start after everything enqueued so far on the context's stream (densify, uploads)
+			if (nlanes > 1)
+			{
+				QTB_CUDA(cudaEventRecord(ctx.aux_events[0], ctx.stream));
+				for (int l = 1; l < nlanes; ++l)
+					QTB_CUDA(cudaStreamWaitEvent(lanes[l].stream, ctx.aux_events[0], 0));
+			}
+			unsigned long long *h_gauge = ctx.pinned_gauge(); // pinned: the read-back of one lane must not block the host
+			for (int sweep = 0; sweep < kMaxSweeps; ++sweep)
+			{
+				bool any = false;
+				for (int l = 0; l < nlanes; ++l)
 				{
-					QTB_CUDA(cudaFuncSetAttribute(svd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-					panel_attr_set = true;
-				}
-				for (int sweep = 0; sweep < kMaxSweeps; ++sweep)
-				{
-					for (int t = 0; t < period_max; ++t)
+					Lane &L = lanes[l];
+					if (!L.active)
+						continue;
+					for (int t = 0; t < L.period; ++t)
 					{
-						const int cnt = step_begin[t + 1] - step_begin[t];
+						const int cnt = L.step_begin[t + 1] - L.step_begin[t];
 						if (cnt == 0)
 							continue;
-						const SvdItem *its = d_items + step_begin[t];
+						const SvdItem *its = L.d_items + L.step_begin[t];
 						if (use_panel)
 						{
-							svd_panel_kernel<<<cnt, kPanelThreads, panel_smem, ctx.stream>>>(d_groups, its, X, d_off + sweep);
+							svd_panel_kernel<<<cnt, kPanelThreads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner);
 							ctx.counters[0] += 1;
 							continue;
 						}
-						svd_gram_mma_kernel<<<dim3(nch_max, cnt), 256, 0, ctx.stream>>>(d_groups, its, X, d_gpart, nch_max);
-						svd_eig_kernel<<<cnt, kEigThreads, kEigSmem, ctx.stream>>>(d_groups, its, d_gpart, nch_max, d_rot, d_flags,
-						                                                        d_off + sweep, conv_tol, inner_max, inner_tol);
-						svd_update_mma_kernel<<<dim3((max_rows + kUpdRows - 1) / kUpdRows, cnt), 256, kUpdSmem, ctx.stream>>>(
-						    d_groups, its, X, d_rot, d_flags);
+						svd_gram_mma_kernel<<<dim3(L.nch_max, cnt), 256, 0, L.stream>>>(d_groups, its, X, L.d_gpart, L.nch_max);
+						svd_eig_kernel<<<cnt, kEigThreads, kEigSmem, L.stream>>>(d_groups, its, L.d_gpart, L.nch_max, L.d_rot, L.d_flags,
+						                                                      L.d_off + sweep, conv_tol, inner_max, inner_tol);
+						svd_update_mma_kernel<<<dim3((L.max_rows + kUpdRows - 1) / kUpdRows, cnt), 256, kUpdSmem, L.stream>>>(
+						    d_groups, its, X, L.d_rot, L.d_flags);
 						ctx.counters[0] += 3;
 					}
 					QTB_CUDA(cudaGetLastError());
-					unsigned long long bits = 0;
-					QTB_CUDA(cudaMemcpyAsync(&bits, d_off + sweep, sizeof(bits), cudaMemcpyDeviceToHost, ctx.stream));
-					QTB_CUDA(cudaStreamSynchronize(ctx.stream));
-					double off;
-					std::memcpy(&off, &bits, sizeof(off));
-					if (std::getenv("QTB_SVD_DEBUG"))
-						std::fprintf(stderr, "[qtb svd] sweep %d gauge %.3e (tol %.3e) groups %ld steps %d panel %d\n", sweep, off,
-						             conv_tol, (long)ng, period_max, (int)use_panel);
-					if (off < conv_tol)
-						break;
+					QTB_CUDA(cudaMemcpyAsync(h_gauge + l, L.d_off + sweep, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+					                         L.stream));
 				}
-				if (d_gpart)
+				for (int l = 0; l < nlanes; ++l)
 				{
-					ctx_free(ctx, d_gpart);
-					ctx_free(ctx, d_rot);
-					ctx_free(ctx, d_flags);
+					Lane &L = lanes[l];
+					if (!L.active)
+						continue;
+					QTB_CUDA(cudaStreamSynchronize(L.stream));
+					double off;
+					std::memcpy(&off, h_gauge + l, sizeof(off));
+					if (std::getenv("QTB_SVD_DEBUG"))
+						std::fprintf(stderr, "[qtb svd] sweep %d lane %d/%d gauge %.3e (tol %.3e) groups %ld of %ld steps %d panel %d\n",
+						             sweep, l, nlanes, off, conv_tol, (long)L.groups.size(), (long)ng, L.period, (int)use_panel);
+					if (off < conv_tol)
+						L.active = false;
+					else
+						any = true;
 				}
-				ctx_free(ctx, d_items);
-				ctx_free(ctx, d_off);
+				if (!any)
+					break;
+			}
+			// join: what follows on the context's stream (column norms, scatter) sees every lane's result
+			for (int l = 1; l < nlanes; ++l)
+			{
+				QTB_CUDA(cudaEventRecord(ctx.aux_events[l], lanes[l].stream));
+				QTB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.aux_events[l], 0));
+			}
+			for (auto &L : lanes)
+			{
+				if (L.d_gpart)
+				{
+					ctx_free(ctx, L.d_gpart);
+					ctx_free(ctx, L.d_rot);
+					ctx_free(ctx, L.d_flags);
+				}
+				if (L.d_items)
+					ctx_free(ctx, L.d_items);
+				if (L.d_off)
+					ctx_free(ctx, L.d_off);
 			}
 		}
 		{
