@@ -1098,6 +1098,8 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	(void)n64;
 	// 128x128 tiles when they fill the machine and do not waste much on block edges
 	plan->tile_cfg = (n128 >= ctx.sm_count && pad128 <= 1.25 * pad64) ? 1 : 0;
+	if (const char *force = std::getenv("QTB_TILE")) // experiment switch: 64 / 128
+		plan->tile_cfg = std::atoi(force) == 128 ? 1 : 0;
 	// skinny: every product is [M x K].[K x N] with K, N <= 16 (contraction with the MPO): CUDA-core row kernel
 	{
 		int max_n = 0, max_k = 0;

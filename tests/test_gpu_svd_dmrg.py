@@ -88,13 +88,16 @@ def test_svd_larger_groups_and_splits(engine):
 
 
 @pytest.mark.parametrize("graded", [False, True])
-def test_svd_large_panel_path(engine, graded):
-    """groups of ~450 x 400: panels that do not fit in shared memory -> the tensor-core path (DMMA Gram / two-sided Jacobi
-    eig with descending eigenvalue order / DMMA update). Random blocks and DMRG-like graded blocks (singular values
-    spanning 40 orders of magnitude, numerically rank deficient)."""
+@pytest.mark.parametrize("bonds", [(700, 620), (1500, 1300)])
+def test_svd_large_panel_path(engine, graded, bonds):
+    """bonds (700, 620): groups of ~450 x 400, (m + n) <= 879 rows -> shared-memory panels of 32 columns (block Jacobi
+    with 16-wide column blocks). bonds (1500, 1300): groups of ~950 x 830 -> panels that do not fit in shared memory ->
+    the tensor-core path (DMMA Gram / two-sided Jacobi eig with descending eigenvalue order / DMMA update, the charge
+    groups dealt to lanes on separate CUDA streams). Random blocks and DMRG-like graded blocks (singular values spanning
+    40 orders of magnitude and more, numerically rank deficient)."""
     rng = np.random.default_rng(5)
-    th = wl.rand_like(wl.shape([wl.bond(5, 700, 1.2, 2), wl.SPIN_HALF, wl.SPIN_HALF, wl.conj_leg(wl.bond(5, 620, 1.2, 2))],
-                               (0,)), rng)
+    th = wl.rand_like(wl.shape([wl.bond(5, bonds[0], 1.2, 2), wl.SPIN_HALF, wl.SPIN_HALF,
+                                wl.conj_leg(wl.bond(5, bonds[1], 1.2, 2))], (0,)), rng)
     if graded:
         for k in th["blocks"]:
             blk = th["blocks"][k]

@@ -135,6 +135,26 @@ def test_tdot_errors(engine):
         to_engine(engine, bad)
 
 
+@pytest.mark.parametrize("mpo_sizes", [[1, 1, 1, 1, 1], [3, 2, 1, 2, 3], [5, 7, 4]])
+def test_tdot_with_small_mpo_legs(engine, mpo_sizes):
+    """the MPO step of H_eff.psi / the environment updates: a big intermediate [w, a', s, b] contracted with a tensor
+    whose dims are all small — the skinny streaming kernel (K, N <= 16) — with MPO bond sections of size 1 (Heisenberg,
+    Hubbard) and of size > 1 (a coalesced MPO: K and N > 1, row offsets no longer a single stride)."""
+    rng = np.random.default_rng(31)
+    n = len(mpo_sizes)
+    charges = [(0,), (-2,), (2,), (0,), (0,)][:n]
+    omega = (mpo_sizes, charges)
+    beta = wl.bond(7, 180, 1.4, 2)
+    beta_odd = (beta[0], [(c[0] - 1,) for c in beta[1]])  # the bond on the other side of one spin-1/2 site
+    t1 = wl.rand_like(wl.shape([omega, wl.conj_leg(beta), wl.SPIN_HALF, beta_odd], (0,)), rng)
+    W = wl.rand_like(wl.shape([wl.conj_leg(omega), wl.SPIN_HALF, omega, wl.conj_leg(wl.SPIN_HALF)], (0,)), rng)
+    A, B = to_engine(engine, t1), to_engine(engine, W)
+    C = A.tensordot(B, [0, 2], [0, 3])
+    check_same(C, orc.tensordot(to_oracle(t1), to_oracle(W), [0, 2], [0, 3]))
+    info = A.tensordot_info(B, [0, 2], [0, 3])
+    assert info["flops"] == orc.tensordot_flops(to_oracle(t1), to_oracle(W), [0, 2], [0, 3])
+
+
 def test_heff_and_envs(engine):
     """H_eff.psi and the environment updates are chains of 3 fused contractions (dmrg.cpp:424-531)"""
     qb = engine
