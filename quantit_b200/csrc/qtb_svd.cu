@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 // No Gram matrix is formed at all in this regime (bond dimension up to a few hundred): the rotation angles come from
 // three warp-reduced dot products of the columns themselves.
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPanelJB = 8;          // column-block width of the shared-memory panel path (measured: 8 beats 4, 16 and 32)
 constexpr int kPanelThreads = 1024; // 32 warps = one per disjoint pair of a 64-column round
 constexpr int kPanelInner = 1;      // inner sweeps per visit (measured: 1 beats 2 and 3 by 20-45 % at bond dimension 512-768)
 
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 	const int ld = nrows | 1; // odd leading dimension: lanes walking a column never collide, columns are skewed
 	double *Xg = X + G.x_off;
 	auto gcol = [&](int c) { return c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi); };
-	for (int e = threadIdx.x; e < p * nrows; e += kPanelThreads)
+	for (int e = threadIdx.x; e < p * nrows; e += blockDim.x)
 	{
 		const int c = e / nrows, r = e - c * nrows;
 		sp[c * ld + r] = Xg[(i64)gcol(c) * G.ld + r];
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 		{
 			// pair pw of the round belongs to warp pw mod 32 (panels wider than 64 columns — whole small groups — give a
 			// warp two or more disjoint pairs per round)
-			for (int pw = warp; pw < pe / 2; pw += kPanelThreads / 32)
+			for (int pw = warp; pw < pe / 2; pw += blockDim.x / 32)
 			{
 				int a, b;
 				if (pw == 0)
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 			s_rot = 0;
 		__syncthreads();
 	}
-	for (int e = threadIdx.x; e < p * nrows; e += kPanelThreads)
+	for (int e = threadIdx.x; e < p * nrows; e += blockDim.x)
 	{
 		const int c = e / nrows, r = e - c * nrows;
 		Xg[(i64)gcol(c) * G.ld + r] = sp[c * ld + r];
@@ -998,12 +999,25 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	for (i64 g = 0; g < ng; ++g)
 		cols_max = std::max(cols_max, std::min(groups[g].m, groups[g].n));
 	const int jb_whole = (int)((cols_max + 1) / 2); // two column blocks per group: one panel = the whole matrix
-	if (jb_whole > kJB && (size_t)(rows_max | 1) * 2 * jb_whole * sizeof(double) <= kPanelSmemMax)
+	static const int jb_env = std::getenv("QTB_SVD_JB") ? std::atoi(std::getenv("QTB_SVD_JB")) : 0;
+	// one-panel-per-group mode (QTB_SVD_WHOLE=1): measured slower than narrow block panels (6.6 ms against 3.4 ms per SVD at
+	// bond dimension 200: one CTA per group leaves the machine empty), kept for reference
+	static const bool no_whole = std::getenv("QTB_SVD_WHOLE") == nullptr;
+	auto panel_fits = [&](int w) { return (size_t)(rows_max | 1) * 2 * w * sizeof(double) <= kPanelSmemMax; };
+	if (!no_whole && jb_whole > kJB && panel_fits(jb_whole))
 		jb = jb_whole; // every group fits in ONE shared-memory panel: plain parallel one-sided Jacobi driven to convergence
-		               // inside one CTA per group (n - 1 rounds per sweep instead of 63 rounds x 3 per block-pair visit)
-	else if ((size_t)(rows_max | 1) * 2 * kJB * sizeof(double) > kPanelSmemMax &&
-	         (size_t)(rows_max | 1) * kJB * sizeof(double) <= kPanelSmemMax)
-		jb = kJB / 2;
+		               // inside one CTA per group (n - 1 rounds per sweep, one launch)
+	else
+	{ // shared-memory panels. Narrow column blocks win: more, shorter panel visits keep more SMs busy (the Hestenes
+	  // rounds of one panel are bound by ONE SM's fp64 rate) — measured at bond dimension 256: 19.3 ms (32-wide blocks),
+	  // 11.7 ms (16), 5.0 ms (8, 256-thread CTAs), 5.8 ms (4) per SVD
+		int want = kPanelJB;
+		if (jb_env >= 2 && jb_env <= kJB)
+			want = jb_env;
+		static const i64 panel_rows_max = std::getenv("QTB_SVD_PANEL_ROWS") ? std::atoll(std::getenv("QTB_SVD_PANEL_ROWS")) : 879;
+		if (panel_fits(want) && rows_max <= panel_rows_max)
+			jb = want;
+	}
 	for (i64 g = 0; g < ng; ++g)
 	{
 		const i64 m = groups[g].transposed ? groups[g].n : groups[g].m;
@@ -1103,6 +1117,10 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			// panels that fit in shared memory take the fused Hestenes kernel
 			const size_t panel_smem = (size_t)((max_rows_all | 1)) * 2 * jb * sizeof(double);
 			const bool use_panel = panel_smem <= kPanelSmemMax;
+			// one warp per disjoint column pair of a round (a panel has 2 jb columns), at most 32 warps
+			// small panels: 32 jb threads, so that several panels share an SM; large panels (<= 2 per SM anyway): a full
+			// CTA, the extra warps speed up the panel load / store
+			const int panel_threads = panel_smem <= 56 * 1024 ? std::max(64, std::min(kPanelThreads, 32 * jb)) : kPanelThreads;
 			static bool panel_attr_set = false, big_attr_set = false;
 			static const int panel_inner = std::getenv("QTB_SVD_PANEL_INNER") ? std::atoi(std::getenv("QTB_SVD_PANEL_INNER")) : kPanelInner;
 			static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
@@ -1138,14 +1156,16 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				bool active = true;
 				double load = 0.0;
 			};
-			std::vector<i64> my_groups;
-			for (i64 g = 0; g < ng; ++g)
-				if (mine(g))
-					my_groups.push_back(g);
-			const int nlanes = use_panel ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, my_groups.size()));
+			// Sharded runs: the lanes, their step sequences and the stopping decisions are those of the WHOLE problem on
+			// every rank (a rank merely skips the items of the groups it does not own, and the per-lane gauges are
+			// max-reduced over the ranks after every sweep), so a group is visited exactly as in the single-rank run and
+			// the factorisation is bit-identical whatever the number of ranks.
+			std::vector<i64> all_groups(ng);
+			std::iota(all_groups.begin(), all_groups.end(), i64(0));
+			const int nlanes = use_panel ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, all_groups.size()));
 			std::vector<Lane> lanes(nlanes);
 			{
-				std::vector<i64> order = my_groups;
+				std::vector<i64> order = all_groups;
 				auto weight = [&](i64 g) { return (double)dg[g].nb * dg[g].nb * (double)dg[g].ld + 1.0; };
 				std::stable_sort(order.begin(), order.end(), [&](i64 x, i64 y) { return weight(x) > weight(y); });
 				for (i64 g : order)
@@ -1179,12 +1199,17 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					for (i64 g : L.groups)
 					{
 						const int nb = dg[g].nb;
+						if (!mine(g))
+							continue;
 						if (nb == 1)
 						{
 							if (t == 0)
 								L.items.push_back({(int)g, 0, 0}); // a single block: rotate inside it
 							continue;
 						}
+						// whole cycles only: a group's visiting order is a sequence of complete row-cyclic sweeps
+						if (t >= (L.period / nb) * nb)
+							continue;
 						const int tau = t % nb;
 						for (int bi = 0; bi < nb; ++bi)
 						{
@@ -1205,7 +1230,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					L.max_items = std::max(L.max_items, L.step_begin[t + 1] - L.step_begin[t]);
 				if (L.max_items == 0)
 				{
-					L.active = false;
+					L.active = sharded && !L.groups.empty(); // nothing to run here, but another rank may own this lane's groups
 					continue;
 				}
 				L.d_items = (SvdItem *)ctx_upload(ctx, L.items.data(), L.items.size() * sizeof(SvdItem));
@@ -1232,7 +1257,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				for (int l = 0; l < nlanes; ++l)
 				{
 					Lane &L = lanes[l];
-					if (!L.active)
+					if (!L.active || L.max_items == 0)
 						continue;
 					for (int t = 0; t < L.period; ++t)
 					{
@@ -1242,7 +1267,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 						const SvdItem *its = L.d_items + L.step_begin[t];
 						if (use_panel)
 						{
-							svd_panel_kernel<<<cnt, kPanelThreads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner);
+							svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner);
 							ctx.counters[0] += 1;
 							continue;
 						}
@@ -1257,14 +1282,41 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					QTB_CUDA(cudaMemcpyAsync(h_gauge + l, L.d_off + sweep, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
 					                         L.stream));
 				}
+				std::vector<double> lane_gauge(nlanes, 0.0);
+				for (int l = 0; l < nlanes; ++l)
+				{
+					Lane &L = lanes[l];
+					if (!L.active || L.max_items == 0)
+						continue;
+					QTB_CUDA(cudaStreamSynchronize(L.stream));
+					std::memcpy(&lane_gauge[l], h_gauge + l, sizeof(double));
+				}
+				if (sharded)
+				{ // max over the ranks through the sum-allreduce: every rank fills its own row of a zero matrix
+					const size_t nslot = (size_t)ctx.world * nlanes;
+					double *d_lg = (double *)ctx_alloc(ctx, nslot * sizeof(double));
+					QTB_CUDA(cudaMemsetAsync(d_lg, 0, nslot * sizeof(double), ctx.stream));
+					double *h_lg = reinterpret_cast<double *>(h_gauge) + 16; // pinned words 16.. : staging for the gauge rows
+					QTB_REQUIRE(nslot <= 40, QTB_ERR_INVALID_ARGUMENT, "svd: world x lanes exceeds the gauge staging area");
+					for (int l = 0; l < nlanes; ++l)
+						h_lg[l] = lane_gauge[l];
+					QTB_CUDA(cudaMemcpyAsync(d_lg + (size_t)ctx.rank * nlanes, h_lg, nlanes * sizeof(double), cudaMemcpyHostToDevice,
+					                         ctx.stream));
+					ctx.allreduce(d_lg, (i64)nslot);
+					std::vector<double> all(nslot);
+					QTB_CUDA(cudaMemcpyAsync(all.data(), d_lg, nslot * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+					QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+					ctx_free(ctx, d_lg);
+					for (int l = 0; l < nlanes; ++l)
+						for (int r = 0; r < ctx.world; ++r)
+							lane_gauge[l] = std::max(lane_gauge[l], all[(size_t)r * nlanes + l]);
+				}
 				for (int l = 0; l < nlanes; ++l)
 				{
 					Lane &L = lanes[l];
 					if (!L.active)
 						continue;
-					QTB_CUDA(cudaStreamSynchronize(L.stream));
-					double off;
-					std::memcpy(&off, h_gauge + l, sizeof(off));
+					const double off = lane_gauge[l];
 					if (std::getenv("QTB_SVD_DEBUG"))
 						std::fprintf(stderr, "[qtb svd] sweep %d lane %d/%d gauge %.3e (tol %.3e) groups %ld of %ld steps %d panel %d\n",
 						             sweep, l, nlanes, off, conv_tol, (long)L.groups.size(), (long)ng, L.period, (int)use_panel);
