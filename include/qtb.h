@@ -195,6 +195,17 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
                     const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, double *sweep_energy,
                     double *sweep_seconds, int64_t *sweep_mid_bond);
 
+/* <a|obs|b> (obs != NULL: `obs` holds `length` rank-4 MPO tensors) or <a|b> (obs == NULL) of two bMPS of `length` sites.
+ * Replaces quantit::contract(const bMPS&, const bMPS&, const bMPO&) and contract(const bMPS&, const bMPS&)
+ * (reference include/MPT.h:724-727, sources/MPT.cpp:211-233, 275-292: identity edges on the outer bonds, all-ones on
+ * the outer MPO bonds; b enters conjugated). The reference returns a rank-0 btensor; here the scalar itself. */
+qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_tensor *const *b, qtb_tensor *const *obs,
+                        double *result);
+/* Moves the orthogonality centre of a bMPS from *oc to `target` with untruncated block SVDs; the handles of the sites
+ * that change are replaced in place and *oc is updated. Replaces bMPS::move_oc(int) (reference include/MPT.h:611,
+ * sources/MPT.cpp:75-111). QTB_ERR_INVALID_ARGUMENT when target is outside the chain (std::invalid_argument there). */
+qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *oc, int64_t target);
+
 #ifdef __cplusplus
 }
 #endif

@@ -738,6 +738,64 @@ def trivial_edges(mps: List[BT], mpo: List[BT]):
     return left, right
 
 
+def _eye_edge(a: BT, dim_a: int, b: BT, dim_b: int, h: BT | None, dim_h: int) -> BT:
+    """eye_like(shape_from(A[dim]^-1, B[dim])) (reference btensor.cpp:2444-2458: identity blocks on the allowed (i, i)
+    section pairs), times ones_like(edge_shape_prep(H, dim)) permuted {0,2,1} when an MPO is present
+    (reference MPT.cpp:218-225)."""
+    mods = a.mods
+    if h is None:
+        t = BT([list(a.sec_sizes[dim_a]), list(b.sec_sizes[dim_b])],
+               [[q_inv(q, mods) for q in a.cvals[dim_a]], list(b.cvals[dim_b])], q_neutral(a.nc), {}, mods)
+        for i in range(min(t.nsec)):
+            if t.allowed((i, i)):
+                t.blocks[(i, i)] = np.eye(*t.block_dims((i, i)))
+        return t
+    t = BT([list(a.sec_sizes[dim_a]), list(h.sec_sizes[dim_h]), list(b.sec_sizes[dim_b])],
+           [[q_inv(q, mods) for q in a.cvals[dim_a]], [q_inv(q, mods) for q in h.cvals[dim_h]], list(b.cvals[dim_b])],
+           q_neutral(a.nc), {}, mods)
+    for i in range(min(t.nsec[0], t.nsec[2])):
+        for j in range(t.nsec[1]):
+            if t.allowed((i, j, i)):
+                da, dw, db = t.block_dims((i, j, i))
+                t.blocks[(i, j, i)] = np.einsum("ab,w->awb", np.eye(da, db), np.ones(dw))
+    return t
+
+
+def contract(a: List[BT], b: List[BT], obs: List[BT] | None = None) -> float:
+    """reference contract(const bMPS&, const bMPS&, const bMPO&), sources/MPT.cpp:211-233, and
+    contract(const bMPS&, const bMPS&), :275-292: three (two) tensordots per site, b conjugated, closed with the right
+    edge; returns the value of the rank-0 result."""
+    assert len(a) == len(b)
+    left = _eye_edge(a[0], 0, b[0], 0, obs[0] if obs else None, 0)
+    right = _eye_edge(a[-1], 2, b[-1], 2, obs[-1] if obs else None, 2)
+    for i in range(len(a)):
+        left = tensordot(left, a[i], [0], [0])
+        if obs:
+            left = tensordot(left, obs[i], [0, 2], [0, 3])
+            left = tensordot(left, conj(b[i]), [0, 2], [0, 1])
+        else:
+            left = tensordot(left, conj(b[i]), [0, 1], [0, 1])
+    res = tensordot(left, right, [0, 1, 2], [0, 1, 2]) if obs else tensordot(left, right, [0, 1], [0, 1])
+    return res.item()
+
+
+def move_oc(mps: List[BT], oc: int, target: int) -> int:
+    """reference bMPS::move_oc(int), sources/MPT.cpp:75-111 (in place on the list; returns the new centre)"""
+    if not (0 <= target < len(mps)):
+        raise ValueError(" Proposed orthogonality center falls outside the MPS")
+    while target < oc:
+        u, d, v = svd(mps[oc], 1)
+        mps[oc] = permute(conj(v), [2, 0, 1])
+        mps[oc - 1] = tensordot(mps[oc - 1], mul_bcast(u, d), [2], [0])
+        oc -= 1
+    while target > oc:
+        u, d, v = svd(mps[oc], 2)
+        mps[oc] = u
+        mps[oc + 1] = tensordot(conj(mul_bcast(v, d)), mps[oc + 1], [0], [0])
+        oc += 1
+    return oc
+
+
 def dmrg(mps: List[BT], mpo: List[BT], oc: int, cutoff: float, conv: float, max_bond: int, min_bond: int = 4,
          max_iter: int = 1000, log=None):
     """details::dmrg_impl + generate_env + sweep, dmrg.cpp:92-100,127-142,219-273,370-409. Returns the energy."""

@@ -249,7 +249,7 @@ int main(int argc, char **argv)
 	at::init_num_threads();
 	if (a.empty())
 	{
-		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub> ...");
+		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub|moveoc> ...");
 		return 2;
 	}
 	try
@@ -369,6 +369,29 @@ int main(int argc, char **argv)
 			if (!dir.empty())
 				for (size_t i = 0; i < L; ++i)
 					dump(psi[i], dir + "/psiF_" + std::to_string(i) + ".qtbt");
+		}
+		else if (cmd == "moveoc")
+		{ // moveoc DIR PREFIX L oc target OUTDIR [HDIR] — bMPS::move_oc on DIR/PREFIX_i.qtbt, dumps OUTDIR/psiM_i.qtbt and
+		  // prints contract(psi, psi) (and contract(psi, psi, H) when HDIR holds H_i.qtbt) before / after
+			std::string dir = a[1], prefix = a[2];
+			size_t L = std::stoul(a[3]), oc = std::stoul(a[4]), target = std::stoul(a[5]);
+			std::string out = a[6];
+			std::vector<btensor> sites;
+			for (size_t i = 0; i < L; ++i)
+				sites.push_back(load(dir + "/" + prefix + "_" + std::to_string(i) + ".qtbt"));
+			bMPS psi(sites, oc);
+			std::printf("NORM_BEFORE %.14f\n", contract(psi, psi).item().toDouble());
+			psi.move_oc((int)target);
+			std::printf("OC %zu\nNORM_AFTER %.14f\n", (size_t)psi.orthogonality_center, contract(psi, psi).item().toDouble());
+			if (a.size() > 7)
+			{
+				bMPO H(L);
+				for (size_t i = 0; i < L; ++i)
+					H[i] = load(a[7] + "/H_" + std::to_string(i) + ".qtbt");
+				std::printf("CONTRACT_E %.14f\n", contract(psi, psi, H).item().toDouble());
+			}
+			for (size_t i = 0; i < L; ++i)
+				dump(psi[i], out + "/psiM_" + std::to_string(i) + ".qtbt");
 		}
 		else
 		{

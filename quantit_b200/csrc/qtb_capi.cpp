@@ -498,4 +498,50 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
 	    });
 }
 
+qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_tensor *const *b, qtb_tensor *const *obs,
+                        double *result)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx && a && b && result && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");
+		    std::vector<const Tensor *> A(length), B(length), H(length);
+		    for (int64_t i = 0; i < length; ++i)
+		    {
+			    QTB_REQUIRE(a[i] && b[i] && (!obs || obs[i]), QTB_ERR_INVALID_ARGUMENT, "null tensor handle");
+			    A[i] = a[i]->t.get();
+			    B[i] = b[i]->t.get();
+			    H[i] = obs ? obs[i]->t.get() : nullptr;
+		    }
+		    *result = contract(ctx->c, length, A.data(), B.data(), obs ? H.data() : nullptr);
+	    });
+}
+
+qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *oc, int64_t target)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx && mps && oc && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");
+		    std::vector<std::unique_ptr<Tensor>> psi(length);
+		    for (int64_t i = 0; i < length; ++i)
+		    {
+			    QTB_REQUIRE(mps[i] != nullptr, QTB_ERR_INVALID_ARGUMENT, "null tensor handle");
+			    psi[i] = std::move(mps[i]->t); // ownership moves into the gauge walk and back (also on error)
+		    }
+		    try
+		    {
+			    move_oc(ctx->c, psi, *oc, target);
+		    }
+		    catch (...)
+		    {
+			    for (int64_t i = 0; i < length; ++i)
+				    mps[i]->t = std::move(psi[i]);
+			    throw;
+		    }
+		    for (int64_t i = 0; i < length; ++i)
+			    mps[i]->t = std::move(psi[i]);
+	    });
+}
+
 } // extern "C"

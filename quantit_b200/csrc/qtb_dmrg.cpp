@@ -51,6 +51,135 @@ static std::unique_ptr<Tensor> trivial_edge(Ctx &ctx, const Tensor &state, i64 s
 	return make_tensor(ctx, st, (i64)index.size() / 3, index.data(), data.data());
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// bMPS / bMPO chain contractions and gauge moves (reference sources/MPT.cpp)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+// eye_like(shape_from(A[dim_a]^-1, B[dim_b])) (x) ones_like(edge_shape_prep(H[dim_h])) permuted to [a^-1, w^-1, b]
+// (reference contract(bMPS, bMPS, bMPO), MPT.cpp:218-225; eye_like btensor.cpp:2444-2458: identity blocks on the (i, i)
+// section pairs the selection rule allows). Without an MPO the edge is the rank-2 eye itself (MPT.cpp:285-290).
+std::unique_ptr<Tensor> eye_edge(Ctx &ctx, const Tensor &a, i64 dim_a, const Tensor &b, i64 dim_b, const Tensor *h, i64 dim_h)
+{
+	const i64 nc = a.st.ct.nc;
+	Structure st;
+	st.rank = h ? 3 : 2;
+	st.ct = a.st.ct;
+	st.sel.assign(nc, 0);
+	auto push = [&](const Tensor &t, i64 d, bool inv)
+	{
+		st.nsec.push_back(t.st.nsec[d]);
+		for (i64 s = 0; s < t.st.nsec[d]; ++s)
+		{
+			st.sec_sizes.push_back(t.st.size_of(d, s));
+			for (i64 c = 0; c < nc; ++c)
+				st.cvals.push_back(inv ? st.ct.norm(-t.st.charge_of(d, s)[c], c) : t.st.charge_of(d, s)[c]);
+		}
+	};
+	push(a, dim_a, true);
+	if (h)
+		push(*h, dim_h, true);
+	push(b, dim_b, false);
+	st.finalize();
+	std::vector<i64> index;
+	std::vector<double> data;
+	const i64 n = std::min(a.st.nsec[dim_a], b.st.nsec[dim_b]);
+	const i64 nw = h ? h->st.nsec[dim_h] : 1;
+	for (i64 i = 0; i < n; ++i)
+		for (i64 j = 0; j < nw; ++j)
+		{
+			i64 idx[3];
+			idx[0] = i;
+			if (h)
+			{
+				idx[1] = j;
+				idx[2] = i;
+			}
+			else
+				idx[1] = i;
+			if (!st.allowed(idx))
+				continue;
+			const i64 ra = a.st.size_of(dim_a, i), rb = b.st.size_of(dim_b, i), w = h ? h->st.size_of(dim_h, j) : 1;
+			index.insert(index.end(), idx, idx + st.rank);
+			for (i64 x = 0; x < ra; ++x)
+				for (i64 y = 0; y < w; ++y)
+					for (i64 z = 0; z < rb; ++z)
+						data.push_back(x == z ? 1.0 : 0.0);
+		}
+	return make_tensor(ctx, st, (i64)index.size() / st.rank, index.data(), data.data());
+}
+
+double scalar_of(Ctx &ctx, const Tensor &t)
+{ // a rank-0 result holds at most the single block {}
+	QTB_REQUIRE(t.st.rank == 0, QTB_ERR_RUNTIME, "contract: the chain did not close to a scalar");
+	if (t.nblocks == 0 || !t.arena || t.arena->numel == 0)
+		return 0.0;
+	double v = 0.0;
+	download(ctx, t, &v);
+	return v;
+}
+} // namespace
+
+double contract(Ctx &ctx, i64 L, const Tensor *const *a, const Tensor *const *b, const Tensor *const *obs)
+{ // reference contract(bMPS, bMPS, bMPO) MPT.cpp:211-233 and contract(bMPS, bMPS) MPT.cpp:275-292
+	QTB_REQUIRE(L >= 1, QTB_ERR_INVALID_ARGUMENT, "contract: empty chain");
+	for (i64 i = 0; i < L; ++i)
+	{
+		QTB_REQUIRE(a[i]->st.rank == 3 && b[i]->st.rank == 3, QTB_ERR_INVALID_ARGUMENT,
+		            "Input bMPT is an invalid bMPS: one or more Tensors has rank differing from 3");
+		QTB_REQUIRE(!obs || obs[i]->st.rank == 4, QTB_ERR_INVALID_ARGUMENT, "contract: MPO tensors must have rank 4");
+	}
+	auto left = eye_edge(ctx, *a[0], 0, *b[0], 0, obs ? obs[0] : nullptr, 0);
+	auto right = eye_edge(ctx, *a[L - 1], 2, *b[L - 1], 2, obs ? obs[L - 1] : nullptr, 2);
+	for (i64 i = 0; i < L; ++i)
+	{
+		auto bc = conj(*b[i]);
+		if (obs)
+		{
+			auto t1 = tensordot(ctx, *left, *a[i], {0}, {0});     // [w, b', s, a]
+			auto t2 = tensordot(ctx, *t1, *obs[i], {0, 2}, {0, 3}); // [b', a, s', w']
+			left = tensordot(ctx, *t2, *bc, {0, 2}, {0, 1});      // [a, w', b'']
+		}
+		else
+		{
+			auto t1 = tensordot(ctx, *left, *a[i], {0}, {0}); // [b', s, a]
+			left = tensordot(ctx, *t1, *bc, {0, 1}, {0, 1});  // [a, b'']
+		}
+	}
+	std::unique_ptr<Tensor> res =
+	    obs ? tensordot(ctx, *left, *right, {0, 1, 2}, {0, 1, 2}) : tensordot(ctx, *left, *right, {0, 1}, {0, 1});
+	return scalar_of(ctx, *res);
+}
+
+void move_oc(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc, i64 target)
+{ // reference bMPS::move_oc, MPT.cpp:75-111
+	const i64 L = (i64)mps.size();
+	QTB_REQUIRE(target >= 0 && target < L, QTB_ERR_INVALID_ARGUMENT,
+	            " Proposed orthogonality center falls outside the MPS");
+	QTB_REQUIRE(oc >= 0 && oc < L, QTB_ERR_INVALID_ARGUMENT,
+	            "orthogonality center position greater than the number of defined tensors.");
+	while (target < oc)
+	{ // svd(curr, 1): curr = (v*) permuted {2,0,1}; previous site absorbs u.d
+		std::unique_ptr<Tensor> u, d, v;
+		block_svd(ctx, *mps[oc], 1, false, 0.0, 0, -1, 2.0, u, d, v);
+		auto vc = conj(*v);
+		mps[oc] = permute(*vc, {2, 0, 1});
+		auto ud = mul_lastdim(ctx, *u, *d);
+		mps[oc - 1] = tensordot(ctx, *mps[oc - 1], *ud, {2}, {0});
+		--oc;
+	}
+	while (target > oc)
+	{ // svd(curr, 2): curr = u; next site absorbs (v.d)*
+		std::unique_ptr<Tensor> u, d, v;
+		block_svd(ctx, *mps[oc], 2, false, 0.0, 0, -1, 2.0, u, d, v);
+		auto vd = mul_lastdim(ctx, *v, *d);
+		auto dv = conj(*vd);
+		mps[oc] = std::move(u);
+		mps[oc + 1] = tensordot(ctx, *dv, *mps[oc + 1], {0}, {0});
+		++oc;
+	}
+}
+
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
           i64 *sweep_mid_bond)

@@ -28,6 +28,10 @@ std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tens
 void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size,
                double pow, std::unique_ptr<Tensor> &u, std::unique_ptr<Tensor> &d, std::unique_ptr<Tensor> &v);
 // qtb_dmrg.cpp
+// <a|obs|b> (obs != nullptr) or <a|b>: reference contract(bMPS, bMPS[, bMPO]), sources/MPT.cpp:211-233, 275-292
+double contract(Ctx &ctx, i64 L, const Tensor *const *a, const Tensor *const *b, const Tensor *const *obs);
+// reference bMPS::move_oc, sources/MPT.cpp:75-111 (untruncated block SVDs; site tensors are replaced in place)
+void move_oc(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc, i64 target);
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
           i64 *sweep_mid_bond);

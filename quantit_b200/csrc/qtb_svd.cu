@@ -1007,6 +1007,9 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	if (!no_whole && jb_whole > kJB && panel_fits(jb_whole))
 		jb = jb_whole; // every group fits in ONE shared-memory panel: plain parallel one-sided Jacobi driven to convergence
 		               // inside one CTA per group (n - 1 rounds per sweep, one launch)
+	else if (cols_max <= 2 * kJB && panel_fits(kJB))
+		jb = kJB; // small groups (<= 64 columns): one or two blocks per group, the panel kernel holds the whole matrix and
+		          // iterates to convergence inside ONE launch
 	else
 	{ // shared-memory panels. Narrow column blocks win: more, shorter panel visits keep more SMs busy (the Hestenes
 	  // rounds of one panel are bound by ONE SM's fp64 rate) — measured at bond dimension 256: 19.3 ms (32-wide blocks),

@@ -109,6 +109,8 @@ _SIGS = [
     ("qtb_env_right", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_two_sites_update", C.c_int, [vp, vp, vp, vp, vp, p_f64, C.POINTER(vp)]),
     ("qtb_dmrg", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, p_f64, p_f64, p_i64]),
+    ("qtb_contract", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), p_f64]),
+    ("qtb_move_oc", C.c_int, [vp, i64, C.POINTER(vp), p_i64, i64]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 
@@ -491,6 +493,32 @@ def dmrg(hamiltonian: List[BTensor], in_out_state: List[BTensor], options: dmrg_
         log["mid_bond"] = [sb[i] for i in range(ns.value)]
         log["oc"] = occ.value
     return E.value
+
+
+def contract(a: List[BTensor], b: List[BTensor], obs: Optional[List[BTensor]] = None) -> float:
+    """reference quantit::contract(const bMPS&, const bMPS&[, const bMPO&]), MPT.h:724-727: <a|obs|b> or <a|b> (b enters
+    conjugated, identity / all-ones edges on the outer bonds). Returns the scalar."""
+    ctx = a[0].ctx
+    L = len(a)
+    if len(b) != L or (obs is not None and len(obs) != L):
+        raise ValueError("contract: the chains must have the same length")
+    A = (vp * L)(*[t.h for t in a])
+    B = (vp * L)(*[t.h for t in b])
+    H = (vp * L)(*[t.h for t in obs]) if obs is not None else None
+    out = C.c_double()
+    _check(ctx.lib.qtb_contract(ctx.h, L, A, B, H, C.byref(out)))
+    return out.value
+
+
+def move_oc(state: List[BTensor], oc: int, target: int) -> int:
+    """reference bMPS::move_oc(int), MPT.h:611: gauge walk of the orthogonality centre from `oc` to `target` with
+    untruncated block SVDs; the BTensor handles in `state` are updated in place. Returns the new centre."""
+    ctx = state[0].ctx
+    L = len(state)
+    P = (vp * L)(*[t.h for t in state])
+    occ = i64(oc)
+    _check(ctx.lib.qtb_move_oc(ctx.h, L, P, C.byref(occ), int(target)))
+    return int(occ.value)
 
 
 def tensordot_host(a: dict, b: dict, dims_a, dims_b, ctx: Optional[Context] = None):

@@ -99,7 +99,18 @@ def main():
                "E0": [float(l.split()[1]) for l in out.splitlines() if l.startswith("E0")][0],
                "contract_E": [float(l.split()[1]) for l in out.splitlines() if l.startswith("CONTRACT_E")][0],
                "oc": [int(l.split()[1]) for l in out.splitlines() if l.startswith("OC")][0]}
+        rec["norm"] = [float(l.split()[3]) for l in out.splitlines() if l.startswith("CONTRACT_E")][0]
         json.dump(rec, open(os.path.join(d, "reference_run.json"), "w"), indent=1)
+        # ---- bMPS::move_oc on the final MPS: centre 0 -> L-2 (moves right), then L-2 -> 1 (moves left) ----
+        for tag, prefix, oc, target in [("psiM", "psiF", rec["oc"], L - 2), ("psiN", "psiM", L - 2, 1)]:
+            td = os.path.join(d, "_tmp")
+            os.makedirs(td, exist_ok=True)
+            subprocess.run([H, "moveoc", d, prefix, str(L), str(oc), str(target), td, d], check=True, capture_output=True)
+            for i in range(L):
+                os.replace(os.path.join(td, f"psiM_{i}.qtbt"), os.path.join(td, f"{tag}x_{i}.qtbt"))
+            for i in range(L):
+                os.replace(os.path.join(td, f"{tag}x_{i}.qtbt"), os.path.join(d, f"{tag}_{i}.qtbt"))
+            os.rmdir(td)
     tot = sum(os.path.getsize(os.path.join(HERE, x)) for x in os.listdir(HERE) if x.endswith(".qtbt"))
     print("golden fixtures written,", tot, "bytes")
 

@@ -144,3 +144,47 @@ def test_dmrg_against_reference_run(engine, name):
         got = back(psi[i])
         assert got.sec_sizes == want.sec_sizes and got.cvals == want.cvals and got.sel == want.sel, i
         assert sorted(got.blocks) == sorted(want.blocks), i
+
+
+# ---- bMPS chain contractions and gauge moves (reference sources/MPT.cpp:75-111, 211-233, 275-292) ------------------------
+def _chain(name, prefix):
+    import json
+    d = os.path.join(G, name)
+    rec = json.load(open(os.path.join(d, "reference_run.json")))
+    L = rec["L"]
+    return rec, [orc.read_qtbt(os.path.join(d, f"H_{i}.qtbt")) for i in range(L)], \
+        [orc.read_qtbt(os.path.join(d, f"{prefix}_{i}.qtbt")) for i in range(L)]
+
+
+@pytest.mark.parametrize("name", ["dmrg_heis8", "dmrg_hub4"])
+def test_contract_and_move_oc_against_reference_run(engine, name):
+    """contract(psi, psi[, H]) of the reference's final MPS against the values the reference printed; bMPS::move_oc
+    against the reference's own moved chains (bit-exact structure per site, overlap with the reference's chain = 1 to 1e-12)"""
+    qb = engine
+    rec, Ho, psio = _chain(name, "psiF")
+    L = rec["L"]
+    H = [eng(qb, t) for t in Ho]
+    psi = [eng(qb, t) for t in psio]
+    assert abs(qb.contract(psi, psi, H) - rec["contract_E"]) <= 1e-12 * abs(rec["contract_E"])
+    assert abs(qb.contract(psi, psi) - rec.get("norm", 1.0)) <= 1e-12
+
+    def check(prefix):
+        want = _chain(name, prefix)[2]
+        got = [back(t) for t in psi]
+        for a, b in zip(got, want):
+            assert a.sec_sizes == b.sec_sizes and a.cvals == b.cvals and a.sel == b.sel
+            assert sorted(a.blocks) == sorted(b.blocks)
+        # the site tensors are defined up to a sign per bond index; the chains must be the same normalised state
+        assert abs(qb.contract(psi, [eng(qb, t) for t in want]) - 1.0) <= 1e-12
+        assert abs(orc.contract(got, want) - 1.0) <= 1e-12
+
+    oc = qb.move_oc(psi, rec["oc"], L - 2)
+    assert oc == L - 2
+    check("psiM")
+    oc = qb.move_oc(psi, oc, 1)
+    assert oc == 1
+    check("psiN")
+    assert abs(qb.contract(psi, psi, H) - rec["contract_E"]) <= 1e-11 * abs(rec["contract_E"])
+    assert abs(qb.contract(psi, psi) - 1.0) <= 1e-12
+    with pytest.raises(qb.InvalidArgument):
+        qb.move_oc(psi, oc, L)
