@@ -205,6 +205,10 @@ qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_
  * that change are replaced in place and *oc is updated. Replaces bMPS::move_oc(int) (reference include/MPT.h:611,
  * sources/MPT.cpp:75-111). QTB_ERR_INVALID_ARGUMENT when target is outside the chain (std::invalid_argument there). */
 qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *oc, int64_t target);
+/* Compresses the bonds of a bMPO by a left-to-right sweep of truncated block SVDs (tolerance `cutoff`, min size 1, no
+ * maximum, pow 2); the handles are replaced in place. Replaces bMPO::coalesce(btensor::Scalar cutoff) (reference
+ * include/MPT.h:699, sources/MPT.cpp:154-168). */
+qtb_status qtb_coalesce(qtb_ctx *ctx, int64_t length, qtb_tensor **mpo, double cutoff);
 
 #ifdef __cplusplus
 }

@@ -796,6 +796,17 @@ def move_oc(mps: List[BT], oc: int, target: int) -> int:
     return oc
 
 
+def coalesce(mpo: List[BT], cutoff: float) -> List[BT]:
+    """reference bMPO::coalesce(cutoff), sources/MPT.cpp:154-168 (in place on the list): svd(tens, 3, cutoff) is the
+    (tol, pow = 2) overload with min_size 1 and no maximum (btensor_linalg.cpp:811-816)"""
+    for i in range(len(mpo) - 1):
+        tens = permute(mpo[i], [0, 1, 3, 2])
+        U, d, V = svd_trunc(tens, 3, cutoff, 1, 2 ** 62, 2.0)
+        mpo[i + 1] = tensordot(conj(V), mpo[i + 1], [0], [0])
+        mpo[i] = permute(mul_bcast(U, d), [0, 1, 3, 2])
+    return mpo
+
+
 def dmrg(mps: List[BT], mpo: List[BT], oc: int, cutoff: float, conv: float, max_bond: int, min_bond: int = 4,
          max_iter: int = 1000, log=None):
     """details::dmrg_impl + generate_env + sweep, dmrg.cpp:92-100,127-142,219-273,370-409. Returns the energy."""

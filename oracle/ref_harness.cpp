@@ -249,7 +249,7 @@ int main(int argc, char **argv)
 	at::init_num_threads();
 	if (a.empty())
 	{
-		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub|moveoc> ...");
+		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub|moveoc|coalesce> ...");
 		return 2;
 	}
 	try
@@ -369,6 +369,17 @@ int main(int argc, char **argv)
 			if (!dir.empty())
 				for (size_t i = 0; i < L; ++i)
 					dump(psi[i], dir + "/psiF_" + std::to_string(i) + ".qtbt");
+		}
+		else if (cmd == "coalesce")
+		{ // coalesce HDIR L cutoff OUTDIR — bMPO::coalesce on HDIR/H_i.qtbt, dumps OUTDIR/Hc_i.qtbt
+			size_t L = std::stoul(a[2]);
+			double cutoff = std::stod(a[3]);
+			bMPO H(L);
+			for (size_t i = 0; i < L; ++i)
+				H[i] = load(a[1] + "/H_" + std::to_string(i) + ".qtbt");
+			H.coalesce(cutoff);
+			for (size_t i = 0; i < L; ++i)
+				dump(H[i], a[4] + "/Hc_" + std::to_string(i) + ".qtbt");
 		}
 		else if (cmd == "moveoc")
 		{ // moveoc DIR PREFIX L oc target OUTDIR [HDIR] — bMPS::move_oc on DIR/PREFIX_i.qtbt, dumps OUTDIR/psiM_i.qtbt and

@@ -544,4 +544,31 @@ qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *
 	    });
 }
 
+qtb_status qtb_coalesce(qtb_ctx *ctx, int64_t length, qtb_tensor **mpo, double cutoff)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx && mpo && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");
+		    std::vector<std::unique_ptr<Tensor>> H(length);
+		    for (int64_t i = 0; i < length; ++i)
+		    {
+			    QTB_REQUIRE(mpo[i] != nullptr, QTB_ERR_INVALID_ARGUMENT, "null tensor handle");
+			    H[i] = std::move(mpo[i]->t);
+		    }
+		    try
+		    {
+			    coalesce(ctx->c, H, cutoff);
+		    }
+		    catch (...)
+		    {
+			    for (int64_t i = 0; i < length; ++i)
+				    mpo[i]->t = std::move(H[i]);
+			    throw;
+		    }
+		    for (int64_t i = 0; i < length; ++i)
+			    mpo[i]->t = std::move(H[i]);
+	    });
+}
+
 } // extern "C"

@@ -180,6 +180,24 @@ void move_oc(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc, i64 t
 	}
 }
 
+void coalesce(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mpo, double cutoff)
+{ // reference bMPO::coalesce, MPT.cpp:154-168: left-to-right sweep of truncated block SVDs over the MPO bonds
+  // (svd(tens, 3, cutoff): min_size 1, max_size unlimited, pow 2 — btensor_linalg.cpp:811-816)
+	const i64 L = (i64)mpo.size();
+	for (i64 i = 0; i < L; ++i)
+		QTB_REQUIRE(mpo[i]->st.rank == 4, QTB_ERR_INVALID_ARGUMENT, "coalesce: MPO tensors must have rank 4");
+	for (i64 i = 0; i + 1 < L; ++i)
+	{
+		auto tens = permute(*mpo[i], {0, 1, 3, 2});
+		std::unique_ptr<Tensor> u, d, v;
+		block_svd(ctx, *tens, 3, true, cutoff, 1, -1, 2.0, u, d, v);
+		auto ud = mul_lastdim(ctx, *u, *d); // U.mul_(d)
+		auto vc = conj(*v);
+		mpo[i + 1] = tensordot(ctx, *vc, *mpo[i + 1], {0}, {0});
+		mpo[i] = permute(*ud, {0, 1, 3, 2});
+	}
+}
+
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
           i64 *sweep_mid_bond)

@@ -32,6 +32,8 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 double contract(Ctx &ctx, i64 L, const Tensor *const *a, const Tensor *const *b, const Tensor *const *obs);
 // reference bMPS::move_oc, sources/MPT.cpp:75-111 (untruncated block SVDs; site tensors are replaced in place)
 void move_oc(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc, i64 target);
+// reference bMPO::coalesce(cutoff), sources/MPT.cpp:154-168 (MPO tensors replaced in place)
+void coalesce(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mpo, double cutoff);
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
           i64 *sweep_mid_bond);

@@ -111,6 +111,7 @@ _SIGS = [
     ("qtb_dmrg", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, p_f64, p_f64, p_i64]),
     ("qtb_contract", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), p_f64]),
     ("qtb_move_oc", C.c_int, [vp, i64, C.POINTER(vp), p_i64, i64]),
+    ("qtb_coalesce", C.c_int, [vp, i64, C.POINTER(vp), C.c_double]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 
@@ -519,6 +520,16 @@ def move_oc(state: List[BTensor], oc: int, target: int) -> int:
     occ = i64(oc)
     _check(ctx.lib.qtb_move_oc(ctx.h, L, P, C.byref(occ), int(target)))
     return int(occ.value)
+
+
+def coalesce(mpo: List[BTensor], cutoff: float) -> List[BTensor]:
+    """reference bMPO::coalesce(cutoff), MPT.h:699: compresses the MPO bonds with truncated block SVDs, in place (the
+    BTensor handles in `mpo` are updated); returns the list."""
+    ctx = mpo[0].ctx
+    L = len(mpo)
+    P = (vp * L)(*[t.h for t in mpo])
+    _check(ctx.lib.qtb_coalesce(ctx.h, L, P, float(cutoff)))
+    return mpo
 
 
 def tensordot_host(a: dict, b: dict, dims_a, dims_b, ctx: Optional[Context] = None):

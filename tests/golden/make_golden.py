@@ -111,6 +111,8 @@ def main():
             for i in range(L):
                 os.replace(os.path.join(td, f"{tag}x_{i}.qtbt"), os.path.join(d, f"{tag}_{i}.qtbt"))
             os.rmdir(td)
+        # ---- bMPO::coalesce(1e-10) of the MPO: Hc_i.qtbt ----
+        subprocess.run([H, "coalesce", d, str(L), "1e-10", d], check=True, capture_output=True)
     tot = sum(os.path.getsize(os.path.join(HERE, x)) for x in os.listdir(HERE) if x.endswith(".qtbt"))
     print("golden fixtures written,", tot, "bytes")
 

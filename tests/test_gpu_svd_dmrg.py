@@ -188,3 +188,22 @@ def test_contract_and_move_oc_against_reference_run(engine, name):
     assert abs(qb.contract(psi, psi) - 1.0) <= 1e-12
     with pytest.raises(qb.InvalidArgument):
         qb.move_oc(psi, oc, L)
+
+
+@pytest.mark.parametrize("name", ["dmrg_heis8", "dmrg_hub4"])
+def test_coalesce_against_reference_run(engine, name):
+    """bMPO::coalesce(1e-10) against the reference's own coalesced MPO: bit-exact structure per site, the operator through
+    gauge-invariant matrix elements <a|H|b> on the run's initial and final states (1e-12)"""
+    qb = engine
+    rec, Ho, psiFo = _chain(name, "psiF")
+    L = rec["L"]
+    Hco = [orc.read_qtbt(os.path.join(G, name, f"Hc_{i}.qtbt")) for i in range(L)]
+    psi0o = _chain(name, "psi0")[2]
+    H = qb.coalesce([eng(qb, t) for t in Ho], 1e-10)
+    for a, b in zip([back(t) for t in H], Hco):
+        assert a.sec_sizes == b.sec_sizes and a.cvals == b.cvals and a.sel == b.sel
+        assert sorted(a.blocks) == sorted(b.blocks)
+    psiF, psi0 = [eng(qb, t) for t in psiFo], [eng(qb, t) for t in psi0o]
+    for (x, y), (xo, yo) in zip(((psiF, psiF), (psi0, psiF), (psi0, psi0)), ((psiFo, psiFo), (psi0o, psiFo), (psi0o, psi0o))):
+        want = orc.contract(xo, yo, Hco)
+        assert abs(qb.contract(x, y, H) - want) <= 1e-12 * max(1.0, abs(want))
