@@ -773,13 +773,6 @@ std::vector<int32_t> flat_offsets(const Tensor &t, i64 b, const std::vector<i64>
 	}
 	return out;
 }
-bool unit_stride(const std::vector<int32_t> &o)
-{
-	for (size_t i = 1; i < o.size(); ++i)
-		if (o[i] - o[i - 1] != 1)
-			return false;
-	return true;
-}
 } // namespace
 
 static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a_in,
@@ -993,7 +986,6 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	};
 
 	// ---- group into output blocks ----
-	bool need_zero = false;
 	size_t pos = 0;
 	std::vector<i64> Ms, Ns;
 	while (pos < cands.size())
@@ -1049,8 +1041,6 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			plan->flops += 2 * M * N * Ka;
 		}
 		go.pair_end = (int32_t)plan->pairs.size();
-		if (go.pair_end == go.pair_begin && M * N > 0)
-			need_zero = true;
 		{
 			i64 ksum = 0;
 			for (int p = go.pair_begin; p < go.pair_end; ++p)
@@ -1072,7 +1062,6 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 		plan->outs[ob].c_off = out.offs[ob];
 	}
 	out.compute_hash();
-	(void)need_zero;
 
 	// ---- tiling ----
 	auto count_tiles = [&](int bm, int bn, double &padded)
@@ -1220,7 +1209,7 @@ void Ctx::prof_dump(const char *title)
 std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
                                   const std::vector<i64> &dims_b)
 {
-	std::chrono::steady_clock::time_point t0, t1;
+	std::chrono::steady_clock::time_point t0;
 	const i64 built0 = ctx.counters[2];
 	if (ctx.prof_level >= 2)
 	{
@@ -1228,8 +1217,6 @@ std::unique_ptr<Tensor> tensordot(Ctx &ctx, const Tensor &a, const Tensor &b, co
 		t0 = std::chrono::steady_clock::now();
 	}
 	auto plan = get_plan(ctx, a, b, dims_a, dims_b);
-	if (ctx.prof_level >= 2)
-		t1 = std::chrono::steady_clock::now();
 	auto out = std::make_unique<Tensor>(plan->out_proto);
 	out->arena = std::make_shared<Arena>(&ctx, plan->out_numel);
 	std::chrono::steady_clock::time_point t1a;

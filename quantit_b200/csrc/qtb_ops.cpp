@@ -180,7 +180,7 @@ std::unique_ptr<Tensor> mul_lastdim(Ctx &ctx, const Tensor &a, const Tensor &d_i
 		s.a_col_stride = 1;
 		s.d_off = d.offs[db];
 		s.o_off = out->offs[ob];
-		if (s.rows * s.n)
+		if (s.rows > 0 && s.n > 0)
 			segs.push_back(s);
 	}
 	launch_mul_lastdim(ctx, segs, ap.arena->ptr, d.arena->ptr, out->arena->ptr);

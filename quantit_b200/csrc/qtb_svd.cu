@@ -986,7 +986,6 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	std::vector<SvdGroup> dg(ng);
 	std::vector<int> sig_off(ng);
 	i64 xtotal = 0, sig_total = 0;
-	int max_nb = 0;
 	// column-block width: the fused shared-memory panel kernel needs (m + n) x 2 jb doubles per panel. Up to 439 rows that
 	// fits with jb = 32; up to 879 rows with jb = 16 (bond dimensions up to ~900: the three-kernel tensor-core path costs
 	// >= 0.3 ms per round-robin step whatever the size, the panel kernel a few tens of microseconds).
@@ -1032,7 +1031,6 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		dg[g].ld = (int)(m + n);
 		dg[g].jb = jb;
 		dg[g].nb = (int)((n + jb - 1) / jb);
-		max_nb = std::max(max_nb, dg[g].nb);
 		sig_off[g] = (int)sig_total;
 		sig_total += n;
 		xtotal += (m + n) * n;
@@ -1102,7 +1100,6 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		}
 
 		// ---- batched block Jacobi ----
-		if (max_nb > 1 || true)
 		{
 			// Ordering: step tau of group g holds the disjoint block pairs (i, j), i < j, with (i + j - 1) mod nb_g == tau.
 			// Run cyclically this is exactly the row-cyclic sweep (0,1),(0,2),...,(0,nb-1),(1,2),... executed as a
