@@ -249,7 +249,7 @@ int main(int argc, char **argv)
 	at::init_num_threads();
 	if (a.empty())
 	{
-		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub|moveoc|coalesce> ...");
+		std::puts("usage: ref_harness <tdot|permute|conj|svd|svdt|heff|lenv|renv|update|mul|heis|hub|moveoc|coalesce|eigh> ...");
 		return 2;
 	}
 	try
@@ -369,6 +369,15 @@ int main(int argc, char **argv)
 			if (!dir.empty())
 				for (size_t i = 0; i < L; ++i)
 					dump(psi[i], dir + "/psiF_" + std::to_string(i) + ".qtbt");
+		}
+		else if (cmd == "eigh")
+		{ // eigh A split OUT_d OUT_U
+			auto A = load(a[1]);
+			size_t split = std::stoul(a[2]);
+			auto [d, U] = quantit::eigh(A, split);
+			dump(d, a[3]);
+			dump(U, a[4]);
+			timed(reps, [&]() { auto X = quantit::eigh(A, split); });
 		}
 		else if (cmd == "coalesce")
 		{ // coalesce HDIR L cutoff OUTDIR — bMPO::coalesce on HDIR/H_i.qtbt, dumps OUTDIR/Hc_i.qtbt
