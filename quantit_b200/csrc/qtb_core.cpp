@@ -40,9 +40,12 @@ Ctx::~Ctx()
 void Ctx::ensure_aux_streams(int n)
 {
 	while ((int)aux_streams.size() < n)
-	{
+	{ // aux stream 0 gets the greatest priority (the heaviest SVD lane runs there: its kernels are the critical path and
+	  // must not queue behind the other lanes' GEMMs), the others the least
+		int least = 0, greatest = 0;
+		QTB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
 		cudaStream_t st = nullptr;
-		QTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+		QTB_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, aux_streams.empty() ? greatest : least));
 		aux_streams.push_back(st);
 	}
 	while (aux_events.size() < aux_streams.size() + 1)

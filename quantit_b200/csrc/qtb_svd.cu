@@ -1178,11 +1178,14 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					lanes[best].load += weight(g);
 				}
 			}
-			ctx.ensure_aux_streams(nlanes - 1);
+			// one lane: the context's stream itself. Several lanes: each on its own auxiliary stream, lane 0 (the heaviest,
+			// LPT order) on the high-priority one; the context's stream only forks and joins.
+			if (nlanes > 1)
+				ctx.ensure_aux_streams(nlanes);
 			for (int l = 0; l < nlanes; ++l)
 			{
 				Lane &L = lanes[l];
-				L.stream = l == 0 ? ctx.stream : ctx.aux_streams[l - 1];
+				L.stream = nlanes == 1 ? ctx.stream : ctx.aux_streams[l];
 				std::sort(L.groups.begin(), L.groups.end());
 				int max_m_l = 1;
 				for (i64 g : L.groups)
@@ -1246,9 +1249,9 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			// fork: the lanes start after everything enqueued so far on the context's stream (densify, uploads)
 			if (nlanes > 1)
 			{
-				QTB_CUDA(cudaEventRecord(ctx.aux_events[0], ctx.stream));
-				for (int l = 1; l < nlanes; ++l)
-					QTB_CUDA(cudaStreamWaitEvent(lanes[l].stream, ctx.aux_events[0], 0));
+				QTB_CUDA(cudaEventRecord(ctx.aux_events[nlanes], ctx.stream));
+				for (int l = 0; l < nlanes; ++l)
+					QTB_CUDA(cudaStreamWaitEvent(lanes[l].stream, ctx.aux_events[nlanes], 0));
 			}
 			unsigned long long *h_gauge = ctx.pinned_gauge(); // pinned: the read-back of one lane must not block the host
 			for (int sweep = 0; sweep < kMaxSweeps; ++sweep)
@@ -1329,7 +1332,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					break;
 			}
 			// join: what follows on the context's stream (column norms, scatter) sees every lane's result
-			for (int l = 1; l < nlanes; ++l)
+			for (int l = 0; l < nlanes && nlanes > 1; ++l)
 			{
 				QTB_CUDA(cudaEventRecord(ctx.aux_events[l], lanes[l].stream));
 				QTB_CUDA(cudaStreamWaitEvent(ctx.stream, ctx.aux_events[l], 0));
