@@ -18,8 +18,9 @@
 //    pipe is not starved by address arithmetic. The producer runs ahead across tile boundaries (it prefetches the next
 //    tile's operands while the consumers finish the current one), which is what keeps the small-block regime
 //    (hundreds of 50x50x50 GEMMs per contraction) from being pipeline-fill bound.
-//  * tiles are assigned statically in a snake order over the planner's cost-sorted list; ragged block edges are
-//    skipped at 8-row/8-column MMA granularity.
+//  * tiles are assigned to the CTAs by the planner (longest-processing-time-first over a cycle model, each CTA's list
+//    heaviest first); work items are self-contained records fetched ahead of use. At ragged block edges a warp tile that
+//    intersects the block is computed whole (clamped rows, zero-filled K tail), a warp tile outside it is skipped.
 #include <cuda_runtime.h>
 
 #include <algorithm>
