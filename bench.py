@@ -385,6 +385,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE JSON line: whatever libraries print while the run is in progress (NCCL writes its
+    # version banner to stdout from C) goes to stderr; the real stdout is kept aside for the final line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: quantit_b200 has no CPU fallback")
@@ -492,7 +498,8 @@ def main():
                                     "ms_per_step": float(np.mean(cms)),
                                     "sample": f"{len(cms)} full {args.workload} contractions on the host CPU "
                                               f"({threads} torch threads), same inputs"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
