@@ -16,8 +16,14 @@ the DMRG-profile D=4096 contraction (T2, 69.5 GFLOP) is timed in the same run an
   cpu_baseline  = the reference's own CPU implementation (oracle/_ref/ref_harness, the unmodified reference sources
            compiled against libtorch) on the box's host cores, same inputs.
 
+  workloads     = side measurements of the same run (N=1): T2, H_eff.psi at D=4096 (three contractions), and two-site
+           DMRG sweeps — Heisenberg L=64 at maximum_bond 256 with the compiled reference's own dmrg() timed on the host
+           next to it, and the BASELINE.json metric's first half, Heisenberg L=100 at maximum_bond 4096
+           (`seconds_last_sweep`; `--dmrg ''` skips the sweeps, which take ~2 of the ~2.5 minutes of a default run).
+
 N>1 (torchrun): the contraction is an independent object per rank (weak scaling, no data-path collective); time is the
-max over ranks of the device time.
+max over ranks of the device time. Under "workloads" ONE H_eff.psi at D=4096 is additionally sharded over the ranks by
+charge sector with one NCCL allreduce (strong scaling). stdout carries exactly one JSON line.
 """
 import argparse
 import json
