@@ -1040,6 +1040,14 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			gp.a_ks = a_aff ? ta.cs : -1;
 			gp.b_ks = b_aff ? tb.rs : -1;
 			gp.b_cs = b_aff ? tb.cs : -1;
+			// bulk-copy staging: the unit-stride runs of an affine operand go through cp.async.bulk (16-byte aligned source:
+			// a run starting on an odd element is fetched from one element earlier, the consumers undo the shift)
+			static const bool bulk_on = !(std::getenv("QTB_BULK") && std::atoi(std::getenv("QTB_BULK")) == 0);
+			gp.shf = 0;
+			if (bulk_on && a_aff && ((gp.a_kcontig && gp.a_ks == 1) || (!gp.a_kcontig && gp.a_rs == 1)))
+				gp.shf |= 1 | (int32_t)((gp.a_off & 1) << 2) | (((gp.a_kcontig ? gp.a_rs : gp.a_ks) & 1) << 3);
+			if (bulk_on && b_aff && ((gp.b_ncontig && gp.b_cs == 1) || (!gp.b_ncontig && gp.b_ks == 1)))
+				gp.shf |= 2 | (int32_t)((gp.b_off & 1) << 4) | (((gp.b_ncontig ? gp.b_ks : gp.b_cs) & 1) << 5);
 			plan->pairs.push_back(gp);
 			plan->flops += 2 * M * N * Ka;
 		}
@@ -1139,7 +1147,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 				{
 					const GemmPair &p0 = plan->pairs[o.pair_begin];
 					plan->tiles.push_back(GemmTile{o.c_off, o.M, o.N, m0, n0, o.pair_begin, o.pair_end, (int32_t)ob, p0.K,
-					                               p0.a_kcontig | (p0.b_ncontig << 1), 0});
+					                               p0.a_kcontig | (p0.b_ncontig << 1), p0.shf});
 				}
 				plan->tile_cost.push_back(c);
 			}

@@ -160,7 +160,7 @@ struct GemmTile
 	int32_t out_blk;              // which output block (sharding filters on it)
 	int32_t K0, flags0;           // K and (a_kcontig | b_ncontig << 1) of the first pair: a single-pair block (every block of
 	                              // configs[1]) needs no pair-descriptor fetch on the consumer side at all
-	int32_t pad_;
+	int32_t shf0;                 // GemmPair::shf of the first pair
 };
 struct GemmOut
 {
@@ -178,7 +178,12 @@ struct GemmPair
 	int32_t b_ncontig;       // 1: n is the unit-stride direction of B (else k is)
 	int32_t a_rs, a_ks;      // affine fast path: offset(m,k) = m*a_rs + k*a_ks   (a_rs < 0: use the tables)
 	int32_t b_ks, b_cs;      // affine fast path: offset(k,n) = k*b_ks + n*b_cs   (b_cs < 0: use the tables)
+	int32_t shf;             // bulk-copy staging (cp.async.bulk, qtb_gemm.cu): bit 0 / 1: operand A / B is staged by 16-byte
+	                         // aligned bulk copies of its unit-stride runs; bit 2 / 4: parity of a_off / b_off; bit 3 / 5:
+	                         // parity of the operand's non-unit stride. A run that starts on an odd element is copied from
+	                         // one element earlier and read back with a one-element shift derived from these parities.
 };
+static_assert(sizeof(GemmPair) == 64, "GemmPair is uploaded as a packed 64-byte record");
 
 constexpr int kSkinnyRows = 1024; // rows of an output block per work item of the skinny (MPO) contraction kernel
 

@@ -50,6 +50,18 @@ __device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar)
 { // the arrival fires when every cp.async issued so far by this thread has landed
 	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{ // adds `bytes` to the transaction count of the current phase (no arrival)
+	asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS UBLKCP): 16-byte aligned source / destination, size a
+// multiple of 16; completion is signalled on the mbarrier as `bytes` transaction bytes.
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gmem, unsigned bytes, unsigned bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+	             "l"(gmem), "r"(bytes), "r"(bar)
+	             : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
 	asm volatile("{\n"
@@ -105,10 +117,12 @@ __device__ __forceinline__ void cp_async8_full(unsigned smem, const void *gmem)
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem), "l"(gmem));
 }
 
+// offpar / strpar: the one-element shift of the bulk-staged layout (GemmPair::shf), 0 / 0 for operands that never take
+// the bulk path: run `i` of the tile (a row for KC, a k index otherwise) is stored shifted by (offpar + i * strpar) & 1.
 template <class Cfg, int R, bool AFF, bool KC, bool FULL>
 __device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__restrict__ base,
                                           const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
-                                          int ks, int r0, int Rmax, int k0, int K, int pt)
+                                          int ks, int r0, int Rmax, int k0, int K, int pt, int offpar, int strpar)
 {
 	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads;
 	constexpr int PER = R * BK / NT;
@@ -119,7 +133,8 @@ __device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__res
 		const bool kok = FULL || (kg < K);
 		const int kc = FULL ? kg : (kok ? kg : 0);
 		const double *src_k = base + (AFF ? (int64_t)kc * ks : (int64_t)ktab[kc]);
-		const unsigned dst = smem_dst + (rbase * (BK + PAD) + k) * 8;
+		static_assert((NT / BK) % 2 == 0, "row parity must be thread-constant");
+		const unsigned dst = smem_dst + (rbase * (BK + PAD) + k + ((offpar + (rbase & 1) * strpar) & 1)) * 8;
 #pragma unroll
 		for (int i = 0; i < PER; ++i)
 		{
@@ -148,10 +163,11 @@ __device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__res
 			const bool kok = FULL || (kg < K);
 			const int kc = FULL ? kg : (kok ? kg : 0);
 			const double *src = src_r + (AFF ? (int64_t)kc * ks : (int64_t)ktab[kc]);
+			const unsigned sh8 = ((offpar + ((kbase + i * (NT / R)) & 1) * strpar) & 1) * 8;
 			if constexpr (FULL)
-				cp_async8_full(dst + i * ((NT / R) * (R + PAD) * 8), src);
+				cp_async8_full(dst + i * ((NT / R) * (R + PAD) * 8) + sh8, src);
 			else
-				cp_async8(dst + i * ((NT / R) * (R + PAD) * 8), src, kok);
+				cp_async8(dst + i * ((NT / R) * (R + PAD) * 8) + sh8, src, kok);
 		}
 	}
 }
@@ -159,7 +175,7 @@ __device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__res
 template <class Cfg, int R>
 __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned smem_dst, const double *__restrict__ base,
                                              const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
-                                             int ks, int r0, int Rmax, int k0, int K, int pt)
+                                             int ks, int r0, int Rmax, int k0, int K, int pt, int offpar, int strpar)
 {
 	const bool full = (r0 + R <= Rmax) && (k0 + Cfg::BK <= K);
 	if (affine)
@@ -167,24 +183,24 @@ __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned sme
 		if (kcontig)
 		{
 			if (full)
-				load_tile<Cfg, R, true, true, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+				load_tile<Cfg, R, true, true, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 			else
-				load_tile<Cfg, R, true, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+				load_tile<Cfg, R, true, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 		}
 		else
 		{
 			if (full)
-				load_tile<Cfg, R, true, false, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+				load_tile<Cfg, R, true, false, true>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 			else
-				load_tile<Cfg, R, true, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+				load_tile<Cfg, R, true, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 		}
 	}
 	else
 	{ // table-driven gather (blocks whose merged free / contracted dims are not a single stride): always bounds-safe
 		if (kcontig)
-			load_tile<Cfg, R, false, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+			load_tile<Cfg, R, false, true, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 		else
-			load_tile<Cfg, R, false, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt);
+			load_tile<Cfg, R, false, false, false>(smem_dst, base, rtab, ktab, rs, ks, r0, Rmax, k0, K, pt, offpar, strpar);
 	}
 }
 
@@ -192,7 +208,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
     grouped_gemm_kernel(const GemmTile *__restrict__ tiles, const int32_t *__restrict__ cta_begin,
                         const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
-                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C)
+                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C, int bulk_mask)
 {
 	constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
 	constexpr int PAD = Cfg::kPad;
@@ -249,15 +265,91 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				const int32_t *bko = offpool + pr.b_koff;
 				const int32_t *bco = offpool + pr.b_coff;
 				const bool a_aff = pr.a_rs >= 0, b_aff = pr.b_cs >= 0;
+				const int shf = pr.shf & bulk_mask;
 				const int nchunk = (pr.K + BK - 1) / BK;
 				for (int ch = 0; ch < nchunk; ++ch)
 				{
 					mbar_wait(empty0 + 8 * stage, phase ^ 1);
 					const unsigned As = smem_u32(smem + stage * Cfg::kStage);
 					const unsigned Bs = As + Cfg::kASize * 8;
+					const unsigned fullb = full0 + 8 * stage;
 					const int k0 = ch * BK;
-					load_operand<Cfg, BM>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt);
-					load_operand<Cfg, BN>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt);
+					// Bulk staging (cp.async.bulk -> UBLKCP, the TMA unit): a K-full chunk of an affine operand is a set of
+					// unit-stride runs (rows of BK elements, or BK runs along the rows); thread `pt` copies run `pt` with ONE
+					// instruction. The source must be 16-byte aligned: a run that starts on an odd element is fetched from one
+					// element earlier and lands shifted by one in its slot (every slot has 4 elements of padding); the consumers
+					// undo the shift from the parities in GemmPair::shf. Rows / columns past the block edge are not copied
+					// (whatever the slot holds only reaches accumulators that are never stored); the K tail chunk takes the
+					// LDGSTS path below, which zero-fills and writes with the same shifts.
+					const bool kfull = k0 + BK <= pr.K;
+					const bool a_bulk = (shf & 1) && kfull, b_bulk = (shf & 2) && kfull;
+					unsigned tx = 0, a_bytes = 0, b_bytes = 0, a_dst = 0, b_dst = 0;
+					const double *a_src = nullptr, *b_src = nullptr;
+					if (a_bulk)
+					{
+						int len;
+						bool valid;
+						if (pr.a_kcontig)
+						{ // run = row m0 + pt, BK elements
+							valid = pt < BM && m0 + pt < M;
+							a_src = Ab + (int64_t)(m0 + pt) * pr.a_rs + k0;
+							len = BK;
+							a_dst = As + pt * (BK + PAD) * 8;
+						}
+						else
+						{ // run = k index k0 + pt, the tile's rows
+							valid = pt < BK;
+							a_src = Ab + (int64_t)(k0 + pt) * pr.a_ks + m0;
+							len = min(BM, M - m0);
+							a_dst = As + pt * (BM + PAD) * 8;
+						}
+						if (valid)
+						{
+							const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(a_src) >> 3) & 1u;
+							a_src -= sh;
+							a_bytes = ((sh + len + 1) >> 1) << 4;
+						}
+					}
+					if (b_bulk)
+					{
+						int len;
+						bool valid;
+						if (pr.b_ncontig)
+						{ // run = k index k0 + pt, the tile's columns
+							valid = pt < BK;
+							b_src = Bb + (int64_t)(k0 + pt) * pr.b_ks + n0;
+							len = min(BN, N - n0);
+							b_dst = Bs + pt * (BN + PAD) * 8;
+						}
+						else
+						{ // run = column n0 + pt, BK elements
+							valid = pt < BN && n0 + pt < N;
+							b_src = Bb + (int64_t)(n0 + pt) * pr.b_cs + k0;
+							len = BK;
+							b_dst = Bs + pt * (BK + PAD) * 8;
+						}
+						if (valid)
+						{
+							const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(b_src) >> 3) & 1u;
+							b_src -= sh;
+							b_bytes = ((sh + len + 1) >> 1) << 4;
+						}
+					}
+					tx = a_bytes + b_bytes;
+					if (tx)
+					{
+						mbar_expect_tx(fullb, tx);
+						if (a_bytes)
+							bulk_g2s(a_dst, a_src, a_bytes, fullb);
+						if (b_bytes)
+							bulk_g2s(b_dst, b_src, b_bytes, fullb);
+					}
+					if (!a_bulk)
+						load_operand<Cfg, BM>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt,
+						                      (shf & 1) ? (shf >> 2) & 1 : 0, (shf & 1) ? (shf >> 3) & 1 : 0);
+					if (!b_bulk)
+						load_operand<Cfg, BN>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt,
+						                      (shf & 2) ? (shf >> 4) & 1 : 0, (shf & 2) ? (shf >> 5) & 1 : 0);
 					mbar_arrive_cp_async(full0 + 8 * stage);
 					if (++stage == STAGES)
 					{
@@ -312,28 +404,34 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				for (int j = 0; j < NI; ++j)
 					acc[i][j][0] = acc[i][j][1] = 0.0;
 
-			int K = ob.K0, lay = ob.flags0;
+			int K = ob.K0, lay = ob.flags0, shf = ob.shf0 & bulk_mask;
 			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
 			{
-				int K_next = 0, lay_next = 0;
+				int K_next = 0, lay_next = 0, shf_next = 0;
 				if (p + 1 < ob.pair_end)
 				{
 					K_next = pairs[p + 1].K;
 					lay_next = pairs[p + 1].a_kcontig | (pairs[p + 1].b_ncontig << 1);
+					shf_next = pairs[p + 1].shf & bulk_mask;
 				}
 				const int a_kc = lay & 1, b_nc = lay >> 1;
 				const int sa_m = a_kc ? (BK + PAD) : 1;
 				const int sa_k = a_kc ? 1 : (BM + PAD);
 				const int sb_k = b_nc ? (BN + PAD) : 1;
 				const int sb_n = b_nc ? 1 : (BK + PAD);
+				// one-element shifts of the bulk-staged runs (see the producer): the run index is the fragment row g (A rows /
+				// B columns when k is the unit-stride direction) or the fragment k index q; every other term of the run's
+				// source address (tile origins, chunk origins, warp and MMA offsets) is even
+				const int shA = (shf & 1) ? (((shf >> 2) & 1) + ((a_kc ? g : q) & 1) * ((shf >> 3) & 1)) & 1 : 0;
+				const int shB = (shf & 2) ? (((shf >> 4) & 1) + ((b_nc ? q : g) & 1) * ((shf >> 5) & 1)) & 1 : 0;
 				const int nchunk = (K + BK - 1) / BK;
 				for (int ch = 0; ch < nchunk; ++ch)
 				{
 					mbar_wait(full0 + 8 * stage, phase);
 					const double *As = smem + stage * Cfg::kStage;
 					const double *Bs = As + Cfg::kASize;
-					const double *Ap = As + (wm0 + g) * sa_m + q * sa_k;
-					const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n;
+					const double *Ap = As + (wm0 + g) * sa_m + q * sa_k + shA;
+					const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n + shB;
 					// A warp whose 32-row x 32-column (64 x 32 for the large configuration) tile intersects the block
 					// computes ALL of it, unpredicated: rows / columns past the block edge were clamped by the producer
 					// (finite data, never stored) and the K tail is zero-filled. The first version skipped invalid 8x8
@@ -369,6 +467,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				}
 				K = K_next;
 				lay = lay_next;
+				shf = shf_next;
 			}
 
 			// epilogue: the output block is a fresh packed row-major [M,N] matrix
@@ -515,8 +614,11 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 		QTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::kThreads, Cfg::kSmemBytes));
 		g_blocks_per_sm[which] = nb > 0 ? nb : 1;
 	}
+	// the bulk-staged layout's shift parities are planned on element offsets: they hold when the arena bases are 16-byte
+	// aligned (always for the engine's own arenas; adopted blocks may not be)
+	const int bulk_mask = ~0 ^ ((reinterpret_cast<uintptr_t>(a) & 15) ? 1 : 0) ^ ((reinterpret_cast<uintptr_t>(b) & 15) ? 2 : 0);
 	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_pairs,
-	                                                            plan.d_offpool, a, b, c);
+	                                                            plan.d_offpool, a, b, c, bulk_mask);
 	QTB_CUDA(cudaGetLastError());
 }
 
