@@ -11,7 +11,10 @@ th = wl.rand_like(wl.shape([beta, wl.SPIN_HALF, wl.SPIN_HALF, wl.conj_leg(beta)]
 if len(sys.argv) > 4:  # decaying spectrum like a real DMRG theta
     for k in th["blocks"]:
         b = th["blocks"][k]; u, s, vt = np.linalg.svd(b.reshape(b.shape[0], -1), full_matrices=False)
-        th["blocks"][k] = ((u * (s * np.exp(-0.15 * np.arange(len(s))))) @ vt).reshape(b.shape)
+        # "decay": exp(-0.15 k) (numerically rank deficient); "span15": log-uniform over 15 decades per block, the profile
+        # of the theta' of a real D=2048 sweep (profiles/r2/s4_dmrg_qr1.txt census lines)
+        prof = np.exp(-0.15 * np.arange(len(s))) if sys.argv[4] == "decay" else 10.0 ** (-15.0 * np.arange(len(s)) / max(len(s) - 1, 1))
+        th["blocks"][k] = ((u * (s[0] * prof)) @ vt).reshape(b.shape)
 T = qb.BTensor.from_host(**th)
 ctx = qb.default_context()
 for i in range(int(os.environ.get("SVD_REPS", "3"))):

@@ -31,6 +31,7 @@
 #include <numeric>
 
 #include "qtb_ops.h"
+#include "qtb_svd_qr.cuh"
 
 namespace qtb
 {
@@ -1017,23 +1018,53 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		if (jb_env >= 2 && jb_env <= kJB)
 			want = jb_env;
 		static const i64 panel_rows_max = std::getenv("QTB_SVD_PANEL_ROWS") ? std::atoll(std::getenv("QTB_SVD_PANEL_ROWS")) : 879;
+		static const int tc_jb = std::getenv("QTB_SVD_TCJB") ? std::atoi(std::getenv("QTB_SVD_TCJB")) : 0;
 		if (panel_fits(want) && rows_max <= panel_rows_max)
 			jb = want;
+		else if (tc_jb >= 8 && tc_jb <= kJB)
+			jb = tc_jb; // experiment switch: narrower column blocks on the tensor-core path
 	}
+	// QR preconditioning (qtb_svd_qr.cuh) on the tensor-core path: the Jacobi iteration then runs on [R^T ; I] (2n x n)
+	const bool use_panel_early = (size_t)((rows_max | 1)) * 2 * jb * sizeof(double) <= kPanelSmemMax;
+	static const bool qr_env = !(std::getenv("QTB_SVD_QR") && std::atoi(std::getenv("QTB_SVD_QR")) == 0);
+	bool use_qr = qr_env && !use_panel_early && ng > 0;
+	for (i64 g = 0; g < ng && use_qr; ++g)
+		if (std::max(groups[g].m, groups[g].n) > (i64)kQrCluster * kQrSlabMax)
+			use_qr = false; // a panel would not fit the cluster's shared memory
+	std::vector<QrGroup> qg(ng);
+	std::vector<i64> fm(ng); // rows of the factorised matrix F_g (m >= n)
 	for (i64 g = 0; g < ng; ++g)
 	{
 		const i64 m = groups[g].transposed ? groups[g].n : groups[g].m;
 		const i64 n = groups[g].transposed ? groups[g].m : groups[g].n;
 		QTB_REQUIRE(m + n < (i64(1) << 31), QTB_ERR_INVALID_ARGUMENT, "svd: group too large");
+		fm[g] = m;
 		dg[g].x_off = xtotal;
-		dg[g].m = (int)m;
+		dg[g].m = (int)(use_qr ? n : m);
 		dg[g].n = (int)n;
-		dg[g].ld = (int)(m + n);
+		dg[g].ld = (int)(use_qr ? 2 * n : m + n);
 		dg[g].jb = jb;
 		dg[g].nb = (int)((n + jb - 1) / jb);
 		sig_off[g] = (int)sig_total;
 		sig_total += n;
-		xtotal += (m + n) * n;
+		xtotal += (i64)dg[g].ld * n;
+		if (use_qr)
+		{
+			QrGroup &q = qg[g];
+			q.m = (int)m;
+			q.n = (int)n;
+			q.x_off = dg[g].x_off;
+			q.a_off = xtotal;
+			xtotal += m * n;
+			q.u_off = xtotal;
+			xtotal += m * n;
+			q.t_off = xtotal;
+			xtotal += ((n + kQrB - 1) / kQrB) * 1024;
+			q.w_off = xtotal;
+			xtotal += ((m + kQrWRows - 1) / kQrWRows) * 32 * n;
+			q.tw_off = xtotal;
+			xtotal += 32 * n;
+		}
 	}
 	std::vector<double> sigma(sig_total, 0.0);
 	std::vector<int> perm(sig_total, 0);
@@ -1064,7 +1095,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				d.rank = (int)r;
 				d.split = (int)split;
 				d.transposed = hg.transposed ? 1 : 0;
-				d.ld = dg[g].ld;
+				d.ld = use_qr ? (int)fm[g] : dg[g].ld;
 				i64 ro = 0, co = 0;
 				for (auto &pr : hg.rows)
 					if (pr.first == info[b].rs)
@@ -1073,7 +1104,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					if (pc.first == info[b].cs)
 						co = pc.second;
 				// A_g(ro.., co..) lives at X(ro, co) or, transposed, X(co, ro)
-				d.dst_off = dg[g].x_off + (hg.transposed ? (co + ro * (i64)d.ld) : (ro + co * (i64)d.ld));
+				d.dst_off = (use_qr ? qg[g].a_off : dg[g].x_off) + (hg.transposed ? (co + ro * (i64)d.ld) : (ro + co * (i64)d.ld));
 				for (i64 k = 0; k < r; ++k)
 				{
 					d.dims[k] = a.dm(b)[k];
@@ -1091,6 +1122,68 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			QTB_CUDA(cudaGetLastError());
 			ctx_free(ctx, d_dd);
 			ctx.counters[0] += 1;
+		}
+		// ---- QR preconditioning: F = Q R (blocked Householder), X = [R^T ; I] ----
+		std::vector<i64> qr_order;
+		QrGroup *d_qr = nullptr;
+		auto qr_count = [&](int k) { // groups (a prefix of qr_order) that still have a panel k
+			int c = 0;
+			while (c < (int)qr_order.size() && (qg[qr_order[c]].n + kQrB - 1) / kQrB > k)
+				++c;
+			return c;
+		};
+		int qr_panels = 0;
+		if (use_qr)
+		{
+			for (i64 g = 0; g < ng; ++g)
+				if (mine(g) && dg[g].n > 0)
+					qr_order.push_back(g);
+			std::stable_sort(qr_order.begin(), qr_order.end(), [&](i64 x, i64 y) { return qg[x].n > qg[y].n; });
+			if (!qr_order.empty())
+			{
+				std::vector<QrGroup> sorted;
+				for (i64 g : qr_order)
+					sorted.push_back(qg[g]);
+				d_qr = (QrGroup *)ctx_upload(ctx, sorted.data(), sorted.size() * sizeof(QrGroup));
+				qr_panels = (qg[qr_order[0]].n + kQrB - 1) / kQrB;
+				static bool qr_attr_set = false;
+				if (!qr_attr_set)
+				{
+					QTB_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					                              (int)qr_panel_smem(kQrSlabMax + 1)));
+					qr_attr_set = true;
+				}
+				for (int k = 0; k < qr_panels; ++k)
+				{
+					const int cnt = qr_count(k), cnt2 = qr_count(k + 1);
+					int max_rows = 0, max_rows2 = 0, max_cols2 = 0;
+					for (int i = 0; i < cnt; ++i)
+					{
+						const QrGroup &q = qg[qr_order[i]];
+						max_rows = std::max(max_rows, q.m - k * kQrB);
+						if (i < cnt2)
+						{
+							max_rows2 = std::max(max_rows2, q.m - k * kQrB);
+							max_cols2 = std::max(max_cols2, q.n - (k + 1) * kQrB);
+						}
+					}
+					const int SP = qr_slab_rows(max_rows) | 1;
+					qr_panel_kernel<<<cnt * kQrCluster, kQrThreads, qr_panel_smem(SP), ctx.stream>>>(d_qr, X, k, SP);
+					ctx.counters[0] += 1;
+					if (cnt2 > 0)
+					{
+						const unsigned ct = (unsigned)((max_cols2 + 63) / 64);
+						qr_w_kernel<<<dim3(ct, (unsigned)((max_rows2 + kQrWRows - 1) / kQrWRows), (unsigned)cnt2), 256, 0, ctx.stream>>>(d_qr, X, k, 0);
+						qr_tw_kernel<<<dim3(ct, (unsigned)cnt2), 256, 0, ctx.stream>>>(d_qr, X, k, 0);
+						qr_apply_kernel<<<dim3(ct, (unsigned)((max_rows2 + kQrARows - 1) / kQrARows), (unsigned)cnt2), 256, 0, ctx.stream>>>(d_qr, X, k, 0);
+						ctx.counters[0] += 3;
+					}
+				}
+				int nmax = qg[qr_order[0]].n;
+				qr_rt_kernel<<<dim3((unsigned)((nmax + 31) / 32), (unsigned)((nmax + 31) / 32), (unsigned)qr_order.size()), 256, 0, ctx.stream>>>(d_qr, X);
+				QTB_CUDA(cudaGetLastError());
+				ctx.counters[0] += 1;
+			}
 		}
 		{
 			dim3 grid(4, (unsigned)std::min<i64>(ng, 4096));
@@ -1358,10 +1451,50 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			ctx.counters[0] += 1;
 			if (sharded)
 				ctx.allreduce(d_sigma, sig_total);
+			if (use_qr && !qr_order.empty())
+			{ // U = Q [J ; 0]: the reflector panels applied in reverse order
+				qr_j_kernel<<<dim3(64, (unsigned)qr_order.size()), 256, 0, ctx.stream>>>(d_qr, X);
+				ctx.counters[0] += 1;
+				for (int k = qr_panels - 1; k >= 0; --k)
+				{
+					const int cnt = qr_count(k);
+					int max_rows = 0, max_cols = 0;
+					for (int i = 0; i < cnt; ++i)
+					{
+						max_rows = std::max(max_rows, qg[qr_order[i]].m - k * kQrB);
+						max_cols = std::max(max_cols, qg[qr_order[i]].n);
+					}
+					const unsigned ct = (unsigned)((max_cols + 63) / 64);
+					qr_w_kernel<<<dim3(ct, (unsigned)((max_rows + kQrWRows - 1) / kQrWRows), (unsigned)cnt), 256, 0, ctx.stream>>>(d_qr, X, k, 1);
+					qr_tw_kernel<<<dim3(ct, (unsigned)cnt), 256, 0, ctx.stream>>>(d_qr, X, k, 1);
+					qr_apply_kernel<<<dim3(ct, (unsigned)((max_rows + kQrARows - 1) / kQrARows), (unsigned)cnt), 256, 0, ctx.stream>>>(d_qr, X, k, 1);
+					ctx.counters[0] += 3;
+				}
+				QTB_CUDA(cudaGetLastError());
+				ctx_free(ctx, d_qr);
+			}
 			QTB_CUDA(cudaMemcpyAsync(sigma.data(), d_sigma, sig_total * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
 			QTB_CUDA(cudaStreamSynchronize(ctx.stream));
 			ctx.counters[5] += sig_total * (i64)sizeof(double);
 		}
+	}
+	if (std::getenv("QTB_SVD_DEBUG") && std::atoi(std::getenv("QTB_SVD_DEBUG")) >= 2 && sig_total > 0)
+	{ // spectrum census of this call
+		double smax = 0;
+		for (double v : sigma)
+			smax = std::max(smax, v);
+		long c6 = 0, c10 = 0, c14 = 0, c16 = 0, nmax = 0;
+		for (double v : sigma)
+		{
+			c6 += v > 1e-6 * smax;
+			c10 += v > 1e-10 * smax;
+			c14 += v > 1e-14 * smax;
+			c16 += v > 1e-16 * smax;
+		}
+		for (i64 g = 0; g < ng; ++g)
+			nmax = std::max<long>(nmax, dg[g].n);
+		std::fprintf(stderr, "[qtb svd] census: %ld values in %ld groups (largest n %ld), > 1e-6: %ld, > 1e-10: %ld, > 1e-14: %ld, > 1e-16: %ld of max %.3e; qr %d\n",
+		             (long)sig_total, (long)ng, nmax, c6, c10, c14, c16, smax, (int)use_qr);
 	}
 	// per group: permutation sorting sigma descending (LAPACK's order)
 	for (i64 g = 0; g < ng; ++g)
@@ -1534,14 +1667,24 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				rows *= T->dm(k)[d];
 			s.rows = (int)rows;
 			s.kept = (int)T->dm(k)[tr - 1];
-			s.ld = dg[e.group].ld;
 			s.group = (int)e.group;
 			s.perm_off = sig_off[e.group];
 			// where do the left (is_u) / right singular vectors live?  not transposed: left = A part, right = rotation
 			// part; transposed (A^T factorised): left = rotation part, right = A part.
 			const bool in_a_part = (is_u != hg.transposed);
-			s.normalize = in_a_part ? 1 : 0;
-			s.src_off = dg[e.group].x_off + (in_a_part ? 0 : dg[e.group].m) + e.off_in_group;
+			if (use_qr)
+			{ // F = (Q J) S W^T: left vectors of F in the U workspace (orthonormal as they are), right vectors = the
+			  // columns of the converged R^T J = W S
+				s.normalize = in_a_part ? 0 : 1;
+				s.ld = in_a_part ? (int)fm[e.group] : dg[e.group].ld;
+				s.src_off = (in_a_part ? qg[e.group].u_off : dg[e.group].x_off) + e.off_in_group;
+			}
+			else
+			{
+				s.normalize = in_a_part ? 1 : 0;
+				s.ld = dg[e.group].ld;
+				s.src_off = dg[e.group].x_off + (in_a_part ? 0 : dg[e.group].m) + e.off_in_group;
+			}
 			if ((i64)s.rows * s.kept > 0 && mine(e.group))
 				sd.push_back(s);
 			++k;
