@@ -7,11 +7,6 @@
 
 using namespace qtb;
 
-namespace qtb
-{
-void ctx_release_ring(Ctx *ctx);
-}
-
 static thread_local std::string g_last_error;
 
 struct qtb_ctx
@@ -46,6 +41,20 @@ static qtb_status guarded(F &&f)
 		g_last_error = e.what();
 		return QTB_ERR_RUNTIME;
 	}
+}
+
+// entry points that take a context: the context's device becomes current first (a process may hold contexts on several
+// devices; kernels, allocations and function attributes are per device)
+template <class F>
+static qtb_status guarded(qtb_ctx *ctx, F &&f)
+{
+	return guarded(
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx != nullptr, QTB_ERR_INVALID_ARGUMENT, "null context");
+		    QTB_CUDA(cudaSetDevice(ctx->c.device));
+		    f();
+	    });
 }
 
 static qtb_tensor *wrap(std::unique_ptr<Tensor> t)
@@ -130,21 +139,20 @@ void qtb_ctx_destroy(qtb_ctx *ctx)
 	cudaSetDevice(ctx->c.device);
 	cudaStreamSynchronize(ctx->c.stream);
 	ctx->c.plan_cache.clear();
-	ctx_release_ring(&ctx->c);
 	delete ctx;
 }
 qtb_status qtb_ctx_sync(qtb_ctx *ctx)
 {
-	return guarded([&]() { QTB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
+	return guarded(ctx, [&]() { QTB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
 }
 qtb_status qtb_ctx_trim(qtb_ctx *ctx)
 {
-	return guarded([&]() { ctx->c.trim_cache(); });
+	return guarded(ctx, [&]() { ctx->c.trim_cache(); });
 }
 void *qtb_ctx_stream(qtb_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
 qtb_status qtb_ctx_counters(qtb_ctx *ctx, int64_t out[8])
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    for (int i = 0; i < 8; ++i)
@@ -156,7 +164,7 @@ qtb_status qtb_tensor_create(qtb_ctx *ctx, int64_t rank, int64_t nc, const int64
                              const int64_t *sec_sizes, const int64_t *cvals, const int64_t *sel, int64_t nblocks,
                              const int64_t *block_index, const double *host_data, qtb_tensor **out)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && out, QTB_ERR_INVALID_ARGUMENT, "null argument");
@@ -170,7 +178,7 @@ qtb_status qtb_tensor_adopt(qtb_ctx *ctx, int64_t rank, int64_t nc, const int64_
                             const int64_t *block_index, void *const *block_ptr, const int64_t *block_strides,
                             qtb_tensor **out)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && out, QTB_ERR_INVALID_ARGUMENT, "null argument");
@@ -255,13 +263,13 @@ qtb_status qtb_tensor_blocks(const qtb_tensor *t, int64_t *index, int64_t *dims,
 }
 qtb_status qtb_tensor_download(qtb_ctx *ctx, const qtb_tensor *t, double *host_out)
 {
-	return guarded([&]() { download(ctx->c, *t->t, host_out); });
+	return guarded(ctx, [&]() { download(ctx->c, *t->t, host_out); });
 }
 
 qtb_status qtb_permute(qtb_ctx *ctx, const qtb_tensor *a, const int64_t *perm, qtb_tensor **out)
 {
 	(void)ctx;
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::vector<i64> p(perm, perm + a->t->st.rank);
@@ -271,13 +279,13 @@ qtb_status qtb_permute(qtb_ctx *ctx, const qtb_tensor *a, const int64_t *perm, q
 qtb_status qtb_conj(qtb_ctx *ctx, const qtb_tensor *a, qtb_tensor **out)
 {
 	(void)ctx;
-	return guarded([&]() { *out = wrap(conj(*a->t)); });
+	return guarded(ctx, [&]() { *out = wrap(conj(*a->t)); });
 }
 
 qtb_status qtb_tensordot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, int64_t k, const int64_t *dims_a,
                          const int64_t *dims_b, qtb_tensor **out)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::vector<i64> da(dims_a, dims_a + k), db(dims_b, dims_b + k);
@@ -288,7 +296,7 @@ qtb_status qtb_tensordot_plan_info(qtb_ctx *ctx, const qtb_tensor *a, const qtb_
                                    const int64_t *dims_a, const int64_t *dims_b, int64_t *n_out_blocks,
                                    int64_t *n_pairs, int64_t *flops)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::vector<i64> da(dims_a, dims_a + k), db(dims_b, dims_b + k);
@@ -304,7 +312,7 @@ qtb_status qtb_tensordot_plan_info(qtb_ctx *ctx, const qtb_tensor *a, const qtb_
 qtb_status qtb_tensordot_into(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, int64_t k,
                               const int64_t *dims_a, const int64_t *dims_b, qtb_tensor *out)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::vector<i64> da(dims_a, dims_a + k), db(dims_b, dims_b + k);
@@ -320,7 +328,7 @@ qtb_status qtb_tensordot_host(qtb_ctx *ctx, int64_t nc, const int64_t *mods, int
                               int64_t k, const int64_t *dims_a, const int64_t *dims_b, int64_t *n_out_blocks,
                               int64_t *c_numel, int64_t *c_index, double *c_data)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::vector<i64> da(dims_a, dims_a + k), db(dims_b, dims_b + k);
@@ -370,15 +378,15 @@ qtb_status qtb_tensordot_host(qtb_ctx *ctx, int64_t nc, const int64_t *mods, int
 qtb_status qtb_axpby(qtb_ctx *ctx, double alpha, const qtb_tensor *a, double beta, const qtb_tensor *b,
                      qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(axpby_dev(ctx->c, nullptr, alpha, *a->t, nullptr, beta, *b->t, false)); });
+	return guarded(ctx, [&]() { *out = wrap(axpby_dev(ctx->c, nullptr, alpha, *a->t, nullptr, beta, *b->t, false)); });
 }
 qtb_status qtb_add(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double alpha, qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(axpby_dev(ctx->c, nullptr, 1.0, *a->t, nullptr, alpha, *b->t, false, alpha)); });
+	return guarded(ctx, [&]() { *out = wrap(axpby_dev(ctx->c, nullptr, 1.0, *a->t, nullptr, alpha, *b->t, false, alpha)); });
 }
 qtb_status qtb_dot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, double *host_out)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    double *d = (double *)ctx_alloc(ctx->c, sizeof(double));
@@ -391,7 +399,7 @@ qtb_status qtb_dot(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *b, doubl
 }
 qtb_status qtb_scale_(qtb_ctx *ctx, qtb_tensor *a, double s)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    Tensor &t = *a->t;
@@ -402,13 +410,13 @@ qtb_status qtb_scale_(qtb_ctx *ctx, qtb_tensor *a, double s)
 }
 qtb_status qtb_mul_lastdim(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *d, qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(mul_lastdim(ctx->c, *a->t, *d->t)); });
+	return guarded(ctx, [&]() { *out = wrap(mul_lastdim(ctx->c, *a->t, *d->t)); });
 }
 
 qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncate, double tol, int64_t min_size,
                    int64_t max_size, double pow, qtb_tensor **u, qtb_tensor **d, qtb_tensor **v)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    std::unique_ptr<Tensor> tu, td, tv;
@@ -421,7 +429,7 @@ qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncat
 
 qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce_fn allreduce, void *user)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx != nullptr, QTB_ERR_INVALID_ARGUMENT, "null context");
@@ -448,22 +456,22 @@ qtb_status qtb_lpt_assign(int64_t n, const double *weights, int world, int32_t *
 qtb_status qtb_heff_apply(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
                           const qtb_tensor *renv, qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(heff_apply(ctx->c, *psi->t, *h2->t, *lenv->t, *renv->t)); });
+	return guarded(ctx, [&]() { *out = wrap(heff_apply(ctx->c, *psi->t, *h2->t, *lenv->t, *renv->t)); });
 }
 qtb_status qtb_env_left(qtb_ctx *ctx, const qtb_tensor *h, const qtb_tensor *mps, const qtb_tensor *lenv,
                         qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(env_left(ctx->c, *h->t, *mps->t, *lenv->t)); });
+	return guarded(ctx, [&]() { *out = wrap(env_left(ctx->c, *h->t, *mps->t, *lenv->t)); });
 }
 qtb_status qtb_env_right(qtb_ctx *ctx, const qtb_tensor *h, const qtb_tensor *mps, const qtb_tensor *renv,
                          qtb_tensor **out)
 {
-	return guarded([&]() { *out = wrap(env_right(ctx->c, *h->t, *mps->t, *renv->t)); });
+	return guarded(ctx, [&]() { *out = wrap(env_right(ctx->c, *h->t, *mps->t, *renv->t)); });
 }
 qtb_status qtb_two_sites_update(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,
                                 const qtb_tensor *renv, double *energy, qtb_tensor **psi_out)
 {
-	return guarded([&]()
+	return guarded(ctx, [&]()
 	               { *psi_out = wrap(two_sites_update(ctx->c, *psi->t, *h2->t, *lenv->t, *renv->t, energy)); });
 }
 
@@ -471,7 +479,7 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
                     const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, double *sweep_energy,
                     double *sweep_seconds, int64_t *sweep_mid_bond)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && mpo && mps && oc && options && energy && n_sweeps, QTB_ERR_INVALID_ARGUMENT, "null argument");
@@ -501,7 +509,7 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
 qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_tensor *const *b, qtb_tensor *const *obs,
                         double *result)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && a && b && result && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");
@@ -519,7 +527,7 @@ qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_
 
 qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *oc, int64_t target)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && mps && oc && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");
@@ -546,7 +554,7 @@ qtb_status qtb_move_oc(qtb_ctx *ctx, int64_t length, qtb_tensor **mps, int64_t *
 
 qtb_status qtb_coalesce(qtb_ctx *ctx, int64_t length, qtb_tensor **mpo, double cutoff)
 {
-	return guarded(
+	return guarded(ctx, 
 	    [&]()
 	    {
 		    QTB_REQUIRE(ctx && mpo && length >= 1, QTB_ERR_INVALID_ARGUMENT, "null argument");

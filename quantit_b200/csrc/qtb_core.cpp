@@ -22,9 +22,14 @@ Ctx::~Ctx()
 {
 	plan_cache.clear();
 	trim_cache();
-	for (auto &kv : live_blocks) // blocks still held by tensors that outlive the context are released with it
+	for (Arena *a : arenas) // tensors that outlive the context: their arenas are orphaned, the blocks released below
+		a->ctx = nullptr;
+	arenas.clear();
+	for (auto &kv : live_blocks)
 		cudaFree(kv.first);
 	live_blocks.clear();
+	if (ring_base)
+		cudaFreeHost(ring_base);
 	if (pinned)
 		cudaFreeHost(pinned);
 	if (pinned_gauge_)
@@ -143,56 +148,36 @@ void ctx_free(Ctx &ctx, void *p)
 	ctx.live_blocks.erase(it);
 }
 
-// Small structure tables go through a pinned ring so that the copy is truly asynchronous; the ring is only recycled
-// after a stream synchronisation.
-namespace
-{
-struct Ring
-{
-	char *base = nullptr;
-	size_t size = 0, pos = 0;
-};
-std::unordered_map<Ctx *, Ring> g_rings;
-} // namespace
-
+// Small structure tables go through a pinned ring (owned by the context) so that the copy is truly asynchronous; the
+// ring is only recycled after a stream synchronisation.
 void *ctx_upload(Ctx &ctx, const void *host, size_t bytes)
 {
 	void *d = ctx_alloc(ctx, bytes);
 	if (bytes == 0)
 		return d;
-	Ring &r = g_rings[&ctx];
 	const size_t need = (bytes + 255) & ~size_t(255);
-	if (r.base == nullptr || need > r.size)
+	if (ctx.ring_base == nullptr || need > ctx.ring_size)
 	{
-		if (r.base)
+		if (ctx.ring_base)
 		{
 			cudaStreamSynchronize(ctx.stream);
-			cudaFreeHost(r.base);
+			cudaFreeHost(ctx.ring_base);
+			ctx.ring_base = nullptr;
 		}
-		r.size = std::max<size_t>(need * 2, size_t(16) << 20);
-		QTB_CUDA(cudaMallocHost((void **)&r.base, r.size));
-		r.pos = 0;
+		ctx.ring_size = std::max<size_t>(need * 2, size_t(16) << 20);
+		QTB_CUDA(cudaMallocHost((void **)&ctx.ring_base, ctx.ring_size));
+		ctx.ring_pos = 0;
 	}
-	if (r.pos + need > r.size)
+	if (ctx.ring_pos + need > ctx.ring_size)
 	{
 		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
-		r.pos = 0;
+		ctx.ring_pos = 0;
 	}
-	std::memcpy(r.base + r.pos, host, bytes);
-	QTB_CUDA(cudaMemcpyAsync(d, r.base + r.pos, bytes, cudaMemcpyHostToDevice, ctx.stream));
-	r.pos += need;
+	std::memcpy(ctx.ring_base + ctx.ring_pos, host, bytes);
+	QTB_CUDA(cudaMemcpyAsync(d, ctx.ring_base + ctx.ring_pos, bytes, cudaMemcpyHostToDevice, ctx.stream));
+	ctx.ring_pos += need;
 	ctx.counters[4] += (i64)bytes;
 	return d;
-}
-void ctx_release_ring(Ctx *ctx)
-{
-	auto it = g_rings.find(ctx);
-	if (it != g_rings.end())
-	{
-		if (it->second.base)
-			cudaFreeHost(it->second.base);
-		g_rings.erase(it);
-	}
 }
 
 Arena::Arena(Ctx *c, i64 n) : numel(n), owned(true), ctx(c)
@@ -200,10 +185,13 @@ Arena::Arena(Ctx *c, i64 n) : numel(n), owned(true), ctx(c)
 	size_t bytes = std::max<i64>(n, 1) * sizeof(double);
 	ptr = (double *)ctx_alloc(*c, bytes);
 	c->counters[7] += (i64)bytes;
+	c->arenas.insert(this);
 }
 Arena::~Arena()
 {
-	if (owned && ptr)
+	if (ctx)
+		ctx->arenas.erase(this);
+	if (owned && ptr && ctx)
 	{
 		ctx_free(*ctx, ptr);
 		ctx->counters[7] -= (i64)(std::max<i64>(numel, 1) * sizeof(double));
@@ -437,11 +425,44 @@ bool Tensor::packed_canonical() const
 			return false;
 	return true;
 }
+static inline uint64_t mix64b(uint64_t h, uint64_t v)
+{ // an independent mixer (splitmix64 finaliser over a different combination) for the second half of the cache key
+	h = (h ^ v) * 0xbf58476d1ce4e5b9ull;
+	h ^= h >> 29;
+	h *= 0x94d049bb133111ebull;
+	h ^= h >> 32;
+	return h + 0x632be59bd9b4e019ull;
+}
 void Tensor::compute_hash()
 {
+	{
+		uint64_t g = 0x9ae16a3b2f90404full;
+		auto eat = [&](const std::vector<i64> &v)
+		{
+			g = mix64b(g, (uint64_t)v.size());
+			for (auto x : v)
+				g = mix64b(g, (uint64_t)x);
+		};
+		g = mix64b(g, (uint64_t)st.rank);
+		g = mix64b(g, (uint64_t)nblocks);
+		g = mix64b(g, (uint64_t)st.ct.nc);
+		eat(st.ct.mods);
+		eat(st.nsec);
+		eat(st.sec_sizes);
+		eat(st.cvals);
+		eat(st.sel);
+		eat(index);
+		eat(dims);
+		eat(strides);
+		eat(offs);
+		layout_hash2 = g;
+	}
 	uint64_t h = 0x1234567ull;
 	h = mix64(h, (uint64_t)st.rank);
 	h = mix64(h, (uint64_t)nblocks);
+	h = mix64(h, (uint64_t)st.ct.nc);
+	for (auto v : st.ct.mods)
+		h = mix64(h, (uint64_t)v + 5);
 	for (auto v : st.nsec)
 		h = mix64(h, (uint64_t)v);
 	for (auto v : st.sec_sizes)
@@ -1193,8 +1214,16 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 		h = mix64(h, (uint64_t)d + 17);
 	for (auto d : dims_b)
 		h = mix64(h, (uint64_t)d + 91);
+	// The cache is keyed by a 128-bit digest: `h` indexes the map, and a hit is only accepted when an independently mixed
+	// second digest of the same layouts (structure, charge type, block tables, offsets, dim lists) agrees as well.
+	uint64_t h2 = mix64b(a.layout_hash2, b.layout_hash2 * 0x9e3779b97f4a7c15ull + 7);
+	h2 = mix64b(h2, dims_a.size());
+	for (auto d : dims_a)
+		h2 = mix64b(h2, (uint64_t)d + 1);
+	for (auto d : dims_b)
+		h2 = mix64b(h2, (uint64_t)d + 1001);
 	auto it = ctx.plan_cache.find(h);
-	if (it != ctx.plan_cache.end())
+	if (it != ctx.plan_cache.end() && it->second->key2 == h2)
 	{
 		ctx.counters[3] += 1;
 		return it->second;
@@ -1202,6 +1231,7 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 	if (ctx.plan_cache.size() > 8192)
 		ctx.plan_cache.clear();
 	auto p = build_plan(ctx, a, b, dims_a, dims_b);
+	p->key2 = h2;
 	ctx.plan_cache[h] = p;
 	return p;
 }

@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/qtb.h"
@@ -114,6 +115,7 @@ struct Tensor
 	std::vector<i64> offs;    // [nblocks] element offsets from arena->ptr
 	std::shared_ptr<Arena> arena;
 	uint64_t layout_hash = 0; // structure-only identity (index/dims/strides/offs): the plan-cache key component
+	uint64_t layout_hash2 = 0; // an independent second hash of the same data: cache hits compare both (128-bit key)
 
 	i64 rank() const { return st.rank; }
 	const i64 *idx(i64 b) const { return &index[b * st.rank]; }
@@ -201,6 +203,7 @@ struct Plan
 	int ncta = 0;
 	std::vector<int32_t> offpool;
 	i64 flops = 0;
+	uint64_t key2 = 0; // second half of the cache key (see get_plan)
 	int tile_cfg = 0; // 0: 64x64 tiles, 1: 128x128 tiles, 2: skinny (one thread per output row, N and K <= 16)
 	int max_n = 0;    // largest N over the output blocks
 	// device copies
@@ -235,6 +238,21 @@ struct Ctx
 	int sm_count = 148;
 	i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	std::unordered_map<uint64_t, std::shared_ptr<Plan>> plan_cache;
+	// live arenas: a context that is destroyed before its tensors orphans them (Arena::ctx = nullptr, the device block is
+	// released with the context) so that a late qtb_tensor_free is harmless
+	std::unordered_set<Arena *> arenas;
+	// pinned ring for small asynchronous uploads (plan tables, descriptors), recycled after a stream synchronisation
+	char *ring_base = nullptr;
+	size_t ring_size = 0, ring_pos = 0;
+	// kernels whose function attributes (dynamic shared memory opt-in, carve-out) were set for this context's device
+	uint32_t kernel_attr_mask = 0;
+	bool attr_once(int bit)
+	{ // true the first time `bit` is asked for
+		if (kernel_attr_mask & (1u << bit))
+			return false;
+		kernel_attr_mask |= 1u << bit;
+		return true;
+	}
 	// caching device allocator (qtb_core.cpp: ctx_alloc / ctx_free)
 	std::map<size_t, std::vector<void *>> free_bins; // size class -> free blocks
 	std::unordered_map<void *, size_t> live_blocks;  // block -> size class

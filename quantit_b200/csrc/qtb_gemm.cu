@@ -600,20 +600,13 @@ __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(c
 using Cfg64 = GemmCfg<64, 64, 16, 32, 32, 5, 2, false>;   // 4 consumer warps + producer warpgroup = 256 threads
 using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + producer warpgroup = 384 threads
 
-static int g_blocks_per_sm[2] = {0, 0};
-
 template <class Cfg>
 static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c,
                        const GemmTile *d_tiles, const int32_t *d_cta_begin, int ncta)
 {
 	auto kern = grouped_gemm_kernel<Cfg>;
-	if (g_blocks_per_sm[which] == 0)
-	{
+	if (ctx.attr_once(which)) // per context (= per device): the opt-in to > 48 KB of dynamic shared memory
 		QTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-		int nb = 0;
-		QTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::kThreads, Cfg::kSmemBytes));
-		g_blocks_per_sm[which] = nb > 0 ? nb : 1;
-	}
 	// the bulk-staged layout's shift parities are planned on element offsets: they hold when the arena bases are 16-byte
 	// aligned (always for the engine's own arenas; adopted blocks may not be)
 	const int bulk_mask = ~0 ^ ((reinterpret_cast<uintptr_t>(a) & 15) ? 1 : 0) ^ ((reinterpret_cast<uintptr_t>(b) & 15) ? 2 : 0);

@@ -640,6 +640,382 @@ __global__ void __launch_bounds__(256) svd_update_mma_kernel(const SvdGroup *__r
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// fused: gram -> eig -> update of one column-block pair in ONE kernel, a thread-block cluster per pair.
+// The three-kernel path above spends 74 % of a DMRG-sized SVD inside svd_eig_kernel (248 us per launch, ~100 CTAs, one per
+// pair: profiles/r2/s6_launches_agg.txt) and its critical path is (steps per sweep) x (gram + eig + update launch
+// latencies). Here the column blocks are 16 wide (a 32 x 32 pair problem: a quarter of the shared-memory traffic per
+// rotation round and half the rounds of the 64 x 64 one), and per round-robin step ONE launch does everything:
+//   1. every CTA of the cluster forms the partial Gram matrix of its slab of panel rows (DMMA) and parks it in L2;
+//   2. cluster barrier; CTA 0 sums the partials in a fixed order (bit-reproducible), measures the pair's gauge and
+//      diagonalises the 32 x 32 matrix by cyclic two-sided Jacobi in shared memory (descending eigenvalue order);
+//   3. cluster barrier; every CTA applies the rotation to its slab of [A;V] rows (DMMA).
+// The cluster barrier is the only inter-CTA synchronisation (the CTAs of a cluster are co-scheduled by the hardware).
+// ---------------------------------------------------------------------------------------------------------------------
+// Rotation (cs, sn) of the fused kernel's eigensolver, written for LATENCY (it is the serial part of every tournament
+// round: measured 2300-3100 cycles per round with the branchy double-precision formulation): the angle is formed in
+// single precision from exactly scaled inputs (3 MUFU operations, no branch), cs and sn are then renormalised in
+// double, (cs, sn) *= 1 + e/2 + 3e^2/8 with e = 1 - cs^2 - sn^2 ~ 1e-7, so that cs^2 + sn^2 = 1 to rounding whatever the
+// accuracy of the angle (an angle good to 1e-7 leaves 1e-7 of the off-diagonal element for the next visit).
+__device__ __forceinline__ void jacobi_cs_fast(double gxx, double gyy, double gxy, double &cs, double &sn)
+{
+	double d = gyy - gxx, o = gxy + gxy;
+	const double mx = fmax(fabs(d), fabs(o));
+	const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+	double t;
+	if (ex == 0 || ex >= 0x7fe)
+	{ // denormal / huge: the textbook formula
+		const double tau = d / o;
+		t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+		cs = 1.0 / sqrt(1.0 + t * t);
+		sn = t * cs;
+		return;
+	}
+	const double scale = __hiloint2double((2046 - ex) << 20, 0); // exact power of two: max(|d|, |o|) lands in [1, 2)
+	const float df = (float)(d * scale), of = (float)(o * scale);
+	float h;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(df, df, of * of)));
+	float tf = __fdividef(of, fabsf(df) + h);
+	if (tf == 0.0f)
+	{ // |o / d| below single-precision range (a column pair 20+ decades apart): t = o / (2 d) in double
+		t = 0.5 * o / d;
+		cs = 1.0; // 1 - t^2 / 2 == 1 in double
+		sn = t;
+		return;
+	}
+	tf = df >= 0.0f ? tf : -tf;
+	const float cf = rsqrtf(fmaf(tf, tf, 1.0f));
+	const double c0 = (double)cf, s0 = (double)(tf * cf);
+	const double e = fma(-c0, c0, fma(-s0, s0, 1.0));
+	const double corr = fma(e, fma(e, 0.375, 0.5), 1.0);
+	cs = c0 * corr;
+	sn = s0 * corr;
+}
+
+constexpr int kFB = 16;                 // column-block width of the fused path
+constexpr int kFP = 2 * kFB;            // panel width
+constexpr int kFCluster = 4;            // CTAs per pair
+constexpr int kFThreads = 256;
+constexpr int kFSub = 64;               // panel rows staged at a time
+constexpr int kFLd = kFSub + 4;         // == 4 mod 16
+constexpr int kFLdJ = kFP + 4;          // == 4 mod 16
+constexpr int kFLdG = kFP + 1;
+
+__global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4)
+    svd_fused_kernel(const SvdGroup *__restrict__ groups, const SvdItem *__restrict__ items, double *__restrict__ X,
+                     double *__restrict__ gpart, double *__restrict__ rot, int *__restrict__ flags,
+                     unsigned long long *offmax, double skip_tol, int inner_max, double inner_tol, long long *dbg)
+{
+	__shared__ double sP[kFP * kFLd];
+	__shared__ double sG[kFP * kFLdG];
+	__shared__ double sJ[kFP * kFLdG];
+	__shared__ double sJ2[kFP * kFLdJ];
+	__shared__ double s_c[kFP / 2], s_s[kFP / 2], s_red[kFThreads / 32];
+	__shared__ int s_rank[kFP];
+	cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+	const int rank = (int)cluster.block_rank();
+	const int item_id = blockIdx.x / kFCluster;
+	const SvdItem it = items[item_id];
+	const SvdGroup G = groups[it.group];
+	const int wi = block_width(G, it.bi), wj = block_width(G, it.bj), p = wi + wj;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+	double *Xg = X + G.x_off;
+	auto gcol = [&](int c) { return c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi); };
+	const int nrows = G.m + G.n;
+	// the rows of the A part (Gram) and of [A;V] (update) are dealt evenly to the CTAs of the cluster
+	const int Sg = (((G.m + kFCluster - 1) / kFCluster) + 7) & ~7, gbeg = min(G.m, rank * Sg), gend = min(G.m, gbeg + Sg);
+	const int S = (((nrows + kFCluster - 1) / kFCluster) + 7) & ~7, sbeg = min(nrows, rank * S), send = min(nrows, sbeg + S);
+	// staging: kFSub rows x kFP columns per pass, fetched into registers one pass ahead of the tensor-core work on the
+	// previous pass (the panel comes from L2 / HBM: the latency of a pass is otherwise exposed twice per pass)
+	constexpr int kPer = kFP * kFSub / kFThreads;
+	auto fetch = [&](int r0, int nr, double (&v)[kPer])
+	{
+#pragma unroll
+		for (int k = 0; k < kPer; ++k)
+		{
+			const int e = tid + k * kFThreads, c = e / kFSub, r = e % kFSub;
+			v[k] = (c < p && r < nr) ? Xg[(i64)gcol(c) * G.ld + r0 + r] : 0.0;
+		}
+	};
+	auto stage = [&](const double (&v)[kPer])
+	{
+#pragma unroll
+		for (int k = 0; k < kPer; ++k)
+		{
+			const int e = tid + k * kFThreads;
+			sP[(e / kFSub) * kFLd + (e % kFSub)] = v[k];
+		}
+	};
+
+	long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+	int dbg_rounds = 0;
+	if (dbg)
+		tq0 = clock64();
+	// ---- 1. partial Gram matrix over this CTA's rows of the A part ----
+	{
+		const int ai = warp >> 1, aj0 = (warp & 1) * 2;
+		double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+		double v[kPer];
+		if (gbeg < gend)
+			fetch(gbeg, min(kFSub, gend - gbeg), v);
+		for (int r0 = gbeg; r0 < gend; r0 += kFSub)
+		{
+			stage(v);
+			__syncthreads();
+			if (r0 + kFSub < gend)
+				fetch(r0 + kFSub, min(kFSub, gend - r0 - kFSub), v);
+#pragma unroll 4
+			for (int kk = 0; kk < kFSub; kk += 4)
+			{
+				const double af = sP[(ai * 8 + g) * kFLd + kk + q];
+#pragma unroll
+				for (int j = 0; j < 2; ++j)
+				{
+					const double bf = sP[((aj0 + j) * 8 + g) * kFLd + kk + q];
+					svd_dmma(acc[j][0], acc[j][1], af, bf);
+				}
+			}
+			__syncthreads();
+		}
+		double *gp = gpart + ((size_t)item_id * kFCluster + rank) * kFP * kFP;
+#pragma unroll
+		for (int j = 0; j < 2; ++j)
+			*reinterpret_cast<double2 *>(gp + (ai * 8 + g) * kFP + (aj0 + j) * 8 + 2 * q) = make_double2(acc[j][0], acc[j][1]);
+	}
+	__threadfence();
+	cluster.sync();
+
+	if (dbg)
+		tq1 = clock64();
+	// ---- 2. CTA 0: gauge + eigen-decomposition of the pair's Gram matrix ----
+	if (rank == 0)
+	{
+		const double *gp = gpart + (size_t)item_id * kFCluster * kFP * kFP;
+		for (int e = tid; e < kFP * kFP; e += kFThreads)
+		{
+			const int i = e / kFP, j = e % kFP;
+			double v = 0.0;
+			if (i < p && j < p)
+#pragma unroll
+				for (int c = 0; c < kFCluster; ++c)
+					v += __ldcg(gp + (size_t)c * kFP * kFP + e);
+			sG[i * kFLdG + j] = v;
+			sJ[i * kFLdG + j] = (i == j) ? 1.0 : 0.0;
+		}
+		__syncthreads();
+		double loc = 0.0;
+		for (int e = tid; e < kFP * kFP; e += kFThreads)
+		{
+			const int i = e / kFP, j = e % kFP;
+			if (i < j && j < p)
+			{
+				const double dd = sG[i * kFLdG + i] * sG[j * kFLdG + j];
+				if (dd > 0.0)
+					loc = fmax(loc, fabs(sG[i * kFLdG + j]) * rsqrt(dd));
+			}
+		}
+		for (int o = 16; o > 0; o >>= 1)
+			loc = fmax(loc, __shfl_xor_sync(0xffffffffu, loc, o));
+		if (lane == 0)
+			s_red[warp] = loc;
+		__syncthreads();
+		double gauge = 0.0;
+		for (int w = 0; w < kFThreads / 32; ++w)
+			gauge = fmax(gauge, s_red[w]);
+		const bool work = gauge > skip_tol;
+		if (tid == 0)
+		{
+			flags[item_id] = work ? 1 : 0;
+			if (gauge > 0.0)
+				atomicMax(offmax, (unsigned long long)__double_as_longlong(gauge));
+		}
+		if (work)
+		{
+			const int pe = (p + 1) & ~1, npair = pe / 2;
+			const int bw = tid >> 4, bq = tid & 15; // this thread's 2x2 block: (pair bw) x (pair bq)
+			auto pair_of = [&](int step, int k, int &x, int &y)
+			{ // tournament: player pe-1 fixed, the others rotate
+				if (k == 0)
+				{
+					x = pe - 1;
+					y = step;
+				}
+				else
+				{
+					x = step + k;
+					x = x >= pe - 1 ? x - (pe - 1) : x;
+					y = step - k;
+					y = y < 0 ? y + (pe - 1) : y;
+				}
+			};
+			// What a sweep leaves of an element of relative size g is ~ g^2: another inner sweep only pays while the elements
+			// met are above inner_tol x the gauge this visit started from (and never below the rotation threshold)
+			const double again_thr = fmax(1e-30, fmin(1e-2, inner_tol * gauge));
+			for (int sweep = 0; sweep < inner_max; ++sweep)
+			{
+				int rotated = 0;
+				for (int step = 0; step < pe - 1; ++step)
+				{
+					++dbg_rounds;
+					long long ta = 0;
+					if (dbg)
+						ta = clock64();
+					// A: the rotations of the round, pair ak on lane ak / 8 of warp ak % 8 (spread over the warps: lanes of one
+					// warp taking different branches of the angle computation would be serialised)
+					const int ak = lane < 2 ? warp + 8 * lane : kFP;
+					if (ak < npair)
+					{
+						int x, y;
+						pair_of(step, ak, x, y);
+						double cs = 1.0, sn = 0.0;
+						if (x < p && y < p)
+						{
+							const double gxy = sG[x * kFLdG + y], gxx = sG[x * kFLdG + x], gyy = sG[y * kFLdG + y];
+							const double sc2 = fabs(gxx * gyy), g2 = gxy * gxy;
+							if (g2 > 1e-34 * sc2 && gxy != 0.0)
+							{
+								jacobi_cs_fast(gxx, gyy, gxy, cs, sn);
+								if (g2 >= again_thr * sc2)
+									rotated = 1; // this sweep met an element large enough to warrant another one
+							}
+						}
+						s_c[ak] = cs;
+						s_s[ak] = sn;
+					}
+					if (dbg)
+						tq4 += clock64() - ta; // phase A (thread-local)
+					__syncthreads();
+					if (bw < npair && bq < npair)
+					{ // B: G <- T^T G T on the 2x2 block, J <- J T on two rows
+						int xw, yw, xq, yq;
+						pair_of(step, bw, xw, yw);
+						pair_of(step, bq, xq, yq);
+						const double cw = s_c[bw], sw = s_s[bw], cq = s_c[bq], sq = s_s[bq];
+						if (sw != 0.0 || sq != 0.0)
+						{
+							const double g00 = sG[xw * kFLdG + xq], g01 = sG[xw * kFLdG + yq];
+							const double g10 = sG[yw * kFLdG + xq], g11 = sG[yw * kFLdG + yq];
+							const double h00 = cw * g00 - sw * g10, h01 = cw * g01 - sw * g11; // rows: T_w^T from the left
+							const double h10 = sw * g00 + cw * g10, h11 = sw * g01 + cw * g11;
+							sG[xw * kFLdG + xq] = cq * h00 - sq * h01; // columns: T_q from the right
+							sG[xw * kFLdG + yq] = sq * h00 + cq * h01;
+							sG[yw * kFLdG + xq] = cq * h10 - sq * h11;
+							sG[yw * kFLdG + yq] = sq * h10 + cq * h11;
+						}
+						if (sq != 0.0)
+						{
+#pragma unroll
+							for (int h = 0; h < 2; ++h)
+							{
+								const int r = 2 * bw + h;
+								const double jx = sJ[r * kFLdG + xq], jy = sJ[r * kFLdG + yq];
+								sJ[r * kFLdG + xq] = cq * jx - sq * jy;
+								sJ[r * kFLdG + yq] = sq * jx + cq * jy;
+							}
+						}
+					}
+					__syncthreads();
+				}
+				if (!__syncthreads_or(rotated))
+					break;
+			}
+			__syncthreads();
+			if (tid < kFP)
+			{ // descending eigenvalue order (de Rijk's ordering in block form)
+				const int k = tid;
+				int rk = k;
+				if (k < p)
+				{
+					const double dk = sG[k * kFLdG + k];
+					rk = 0;
+					for (int j = 0; j < p; ++j)
+					{
+						const double dj = sG[j * kFLdG + j];
+						rk += (dj > dk || (dj == dk && j < k)) ? 1 : 0;
+					}
+				}
+				s_rank[k] = rk;
+			}
+			__syncthreads();
+			double *Jm = rot + (size_t)item_id * kFP * kFP;
+			for (int e = tid; e < kFP * kFP; e += kFThreads)
+			{
+				const int i = e / kFP, k = e % kFP;
+				Jm[i * kFP + s_rank[k]] = sJ[i * kFLdG + k];
+			}
+		}
+	}
+	if (dbg)
+		tq2 = clock64();
+	__threadfence();
+	cluster.sync();
+
+	if (dbg)
+	{
+		tq3 = clock64();
+		if (rank == 0 && tid == 0)
+		{
+			dbg[item_id * 8 + 0] = tq1 - tq0;
+			dbg[item_id * 8 + 1] = tq2 - tq1;
+			dbg[item_id * 8 + 2] = tq3 - tq2;
+			dbg[item_id * 8 + 3] = dbg_rounds;
+			dbg[item_id * 8 + 5] = tq4;
+			tq4 = 0;
+		}
+	}
+	// ---- 3. every CTA rotates its rows of the [A;V] panel ----
+	if (!__ldcg(flags + item_id))
+		return;
+	{
+		const double *Jm = rot + (size_t)item_id * kFP * kFP;
+		for (int e = tid; e < kFP * kFP; e += kFThreads)
+			sJ2[(e / kFP) * kFLdJ + (e % kFP)] = __ldcg(Jm + e);
+		const int rw0 = warp * 8;
+		double v[kPer];
+		if (sbeg < send)
+			fetch(sbeg, min(kFSub, send - sbeg), v);
+		for (int r0 = sbeg; r0 < send; r0 += kFSub)
+		{
+			const int nr = min(kFSub, send - r0);
+			__syncthreads(); // the previous pass is done with sP (and, the first time, sJ2 is complete)
+			stage(v);
+			__syncthreads();
+			if (r0 + kFSub < send)
+				fetch(r0 + kFSub, min(kFSub, send - r0 - kFSub), v);
+			double acc[4][2];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+			for (int kk = 0; kk < kFP; kk += 4)
+			{
+				const double af = sP[(kk + q) * kFLd + rw0 + g];
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					svd_dmma(acc[j][0], acc[j][1], af, sJ2[(kk + q) * kFLdJ + j * 8 + g]);
+			}
+			const int r = rw0 + g;
+			if (r < nr)
+			{
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+#pragma unroll
+					for (int h = 0; h < 2; ++h)
+					{
+						const int c = j * 8 + 2 * q + h;
+						if (c < p)
+							Xg[(i64)gcol(c) * G.ld + r0 + r] = acc[j][h];
+					}
+			}
+		}
+	}
+	if (dbg && rank == 0 && tid == 0)
+	{
+		tq4 = clock64();
+		dbg[item_id * 8 + 4] = tq4 - tq3;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // panel: the three kernels above fused for panels that fit in shared memory ((m+n) x p doubles): the (m+n) x (wI+wJ)
 // panel of [A;V] is loaded once, orthogonalised in place by one-sided (Hestenes) Jacobi rotations among its columns —
 // one warp per column pair, 16 disjoint pairs per round, round-robin over the <= 32 columns — and written back.
@@ -1024,6 +1400,10 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		else if (tc_jb >= 8 && tc_jb <= kJB)
 			jb = tc_jb; // experiment switch: narrower column blocks on the tensor-core path
 	}
+	// panels that do not fit in shared memory: the fused cluster kernel (16-wide column blocks) unless switched off
+	static const bool fused_env = !(std::getenv("QTB_SVD_FUSED") && std::atoi(std::getenv("QTB_SVD_FUSED")) == 0);
+	if (fused_env && jb == kJB && !panel_fits(kJB))
+		jb = kFB;
 	// QR preconditioning (qtb_svd_qr.cuh) on the tensor-core path: the Jacobi iteration then runs on [R^T ; I] (2n x n)
 	const bool use_panel_early = (size_t)((rows_max | 1)) * 2 * jb * sizeof(double) <= kPanelSmemMax;
 	static const bool qr_env = !(std::getenv("QTB_SVD_QR") && std::atoi(std::getenv("QTB_SVD_QR")) == 0);
@@ -1146,13 +1526,9 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 					sorted.push_back(qg[g]);
 				d_qr = (QrGroup *)ctx_upload(ctx, sorted.data(), sorted.size() * sizeof(QrGroup));
 				qr_panels = (qg[qr_order[0]].n + kQrB - 1) / kQrB;
-				static bool qr_attr_set = false;
-				if (!qr_attr_set)
-				{
+				if (ctx.attr_once(5))
 					QTB_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					                              (int)qr_panel_smem(kQrSlabMax + 1)));
-					qr_attr_set = true;
-				}
 				for (int k = 0; k < qr_panels; ++k)
 				{
 					const int cnt = qr_count(k), cnt2 = qr_count(k + 1);
@@ -1214,23 +1590,22 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			// small panels: 32 jb threads, so that several panels share an SM; large panels (<= 2 per SM anyway): a full
 			// CTA, the extra warps speed up the panel load / store
 			const int panel_threads = panel_smem <= 56 * 1024 ? std::max(64, std::min(kPanelThreads, 32 * jb)) : kPanelThreads;
-			static bool panel_attr_set = false, big_attr_set = false;
 			static const int panel_inner = std::getenv("QTB_SVD_PANEL_INNER") ? std::atoi(std::getenv("QTB_SVD_PANEL_INNER")) : kPanelInner;
 			static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
 			// inner sweeps stop once the off-diagonal mass they leave (~ g^2) is below inner_tol x the pair's gauge
 			static const double inner_tol = std::getenv("QTB_SVD_INNER_TOL") ? std::atof(std::getenv("QTB_SVD_INNER_TOL")) : 1e-1;
+			static const int fused_inner = std::getenv("QTB_SVD_FINNER") ? std::atoi(std::getenv("QTB_SVD_FINNER")) : 2;
 			static const int lanes_max = std::getenv("QTB_SVD_LANES") ? std::max(1, std::atoi(std::getenv("QTB_SVD_LANES"))) : 4;
-			if (!use_panel && !big_attr_set)
+			if (!use_panel && ctx.attr_once(2))
 			{
 				QTB_CUDA(cudaFuncSetAttribute(svd_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEigSmem));
 				QTB_CUDA(cudaFuncSetAttribute(svd_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdSmem));
-				big_attr_set = true;
 			}
-			if (use_panel && !panel_attr_set)
-			{
+			if (ctx.attr_once(4)) // 44 KB of static shared memory per CTA: the large carve-out lets a whole cluster share an SM
+				QTB_CUDA(cudaFuncSetAttribute(svd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+				                              (int)cudaSharedmemCarveoutMaxShared));
+			if (use_panel && ctx.attr_once(3))
 				QTB_CUDA(cudaFuncSetAttribute(svd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-				panel_attr_set = true;
-			}
 			// Lanes: the charge groups are independent factorisations. On the tensor-core path every round-robin step is
 			// gram -> eig -> update with the eigensolver a ~0.27 ms latency-bound kernel that leaves the tensor cores idle,
 			// so the groups are dealt to a few lanes (LPT over their work), each lane runs its own step sequence on its own
@@ -1255,7 +1630,8 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			// the factorisation is bit-identical whatever the number of ranks.
 			std::vector<i64> all_groups(ng);
 			std::iota(all_groups.begin(), all_groups.end(), i64(0));
-			const int nlanes = use_panel ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, all_groups.size()));
+			const bool use_fused = !use_panel && jb == kFB && fused_env;
+			const int nlanes = (use_panel || use_fused) ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, all_groups.size()));
 			std::vector<Lane> lanes(nlanes);
 			{
 				std::vector<i64> order = all_groups;
@@ -1364,6 +1740,36 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 						if (use_panel)
 						{
 							svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner);
+							ctx.counters[0] += 1;
+							continue;
+						}
+						if (use_fused)
+						{
+							static const bool fdbg = std::getenv("QTB_SVD_DEBUG") && std::atoi(std::getenv("QTB_SVD_DEBUG")) >= 3;
+							long long *d_dbg = nullptr;
+							if (fdbg && t == 0 && (sweep == 0 || sweep == 4))
+							{
+								d_dbg = (long long *)ctx_alloc(ctx, (size_t)cnt * 8 * sizeof(long long));
+								QTB_CUDA(cudaMemsetAsync(d_dbg, 0, (size_t)cnt * 8 * sizeof(long long), L.stream));
+							}
+							svd_fused_kernel<<<cnt * kFCluster, kFThreads, 0, L.stream>>>(d_groups, its, X, L.d_gpart, L.d_rot, L.d_flags,
+							                                                              L.d_off + sweep, conv_tol, fused_inner, inner_tol, d_dbg);
+							if (d_dbg)
+							{
+								std::vector<long long> h((size_t)cnt * 8);
+								QTB_CUDA(cudaMemcpyAsync(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, L.stream));
+								QTB_CUDA(cudaStreamSynchronize(L.stream));
+								double a[6] = {0, 0, 0, 0, 0, 0}, mx[6] = {0, 0, 0, 0, 0, 0};
+								for (int i = 0; i < cnt; ++i)
+									for (int k = 0; k < 6; ++k)
+									{
+										a[k] += (double)h[i * 8 + k] / cnt;
+										mx[k] = std::max(mx[k], (double)h[i * 8 + k]);
+									}
+								std::fprintf(stderr, "[qtb svd] fused phases (cycles, CTA 0 of %d clusters) sweep %d: gram+barrier avg %.0f max %.0f | eig avg %.0f max %.0f | barrier %.0f max %.0f | rounds avg %.1f max %.0f | update avg %.0f max %.0f | phase A total avg %.0f\n",
+								             cnt, sweep, a[0], mx[0], a[1], mx[1], a[2], mx[2], a[3], mx[3], a[4], mx[4], a[5]);
+								ctx_free(ctx, d_dbg);
+							}
 							ctx.counters[0] += 1;
 							continue;
 						}
