@@ -693,14 +693,14 @@ __device__ __forceinline__ void jacobi_cs_fast(double gxx, double gyy, double gx
 
 constexpr int kFB = 16;                 // column-block width of the fused path
 constexpr int kFP = 2 * kFB;            // panel width
-constexpr int kFCluster = 4;            // CTAs per pair
+constexpr int kFClusterMax = 8;         // CTAs per pair: 1, 2, 4 or 8, chosen per call so that a step is one wave
 constexpr int kFThreads = 256;
 constexpr int kFSub = 64;               // panel rows staged at a time
 constexpr int kFLd = kFSub + 4;         // == 4 mod 16
 constexpr int kFLdJ = kFP + 4;          // == 4 mod 16
 constexpr int kFLdG = kFP + 1;
 
-__global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4)
+__global__ void __launch_bounds__(kFThreads, 4)
     svd_fused_kernel(const SvdGroup *__restrict__ groups, const SvdItem *__restrict__ items, double *__restrict__ X,
                      double *__restrict__ gpart, double *__restrict__ rot, int *__restrict__ flags,
                      unsigned long long *offmax, double skip_tol, int inner_max, double inner_tol, long long *dbg)
@@ -713,6 +713,7 @@ __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4
 	__shared__ int s_rank[kFP];
 	cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
 	const int rank = (int)cluster.block_rank();
+	const int kFCluster = (int)cluster.num_blocks(); // launch attribute (cudaLaunchAttributeClusterDimension)
 	const int item_id = blockIdx.x / kFCluster;
 	const SvdItem it = items[item_id];
 	const SvdGroup G = groups[it.group];
@@ -746,7 +747,7 @@ __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4
 		}
 	};
 
-	long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+	long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tqA = 0;
 	int dbg_rounds = 0;
 	if (dbg)
 		tq0 = clock64();
@@ -795,7 +796,6 @@ __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4
 			const int i = e / kFP, j = e % kFP;
 			double v = 0.0;
 			if (i < p && j < p)
-#pragma unroll
 				for (int c = 0; c < kFCluster; ++c)
 					v += __ldcg(gp + (size_t)c * kFP * kFP + e);
 			sG[i * kFLdG + j] = v;
@@ -884,33 +884,35 @@ __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4
 					if (dbg)
 						tq4 += clock64() - ta; // phase A (thread-local)
 					__syncthreads();
+					if (dbg)
+						tqA += clock64() - ta; // phase A as the CTA sees it (slowest warp + barrier)
 					if (bw < npair && bq < npair)
 					{ // B: G <- T^T G T on the 2x2 block, J <- J T on two rows
 						int xw, yw, xq, yq;
 						pair_of(step, bw, xw, yw);
 						pair_of(step, bq, xq, yq);
 						const double cw = s_c[bw], sw = s_s[bw], cq = s_c[bq], sq = s_s[bq];
+						// every load of the round first, every store last: the fp64 / shared-memory latencies of this part are
+						// long (the whole round is a latency chain), so the three independent 2x2 updates must overlap
+						double *g0 = sG + xw * kFLdG, *g1 = sG + yw * kFLdG;
+						double *j0 = sJ + (2 * bw) * kFLdG, *j1 = j0 + kFLdG;
+						const double g00 = g0[xq], g01 = g0[yq], g10 = g1[xq], g11 = g1[yq];
+						const double a0x = j0[xq], a0y = j0[yq], a1x = j1[xq], a1y = j1[yq];
+						const double h00 = cw * g00 - sw * g10, h01 = cw * g01 - sw * g11; // rows: T_w^T from the left
+						const double h10 = sw * g00 + cw * g10, h11 = sw * g01 + cw * g11;
 						if (sw != 0.0 || sq != 0.0)
 						{
-							const double g00 = sG[xw * kFLdG + xq], g01 = sG[xw * kFLdG + yq];
-							const double g10 = sG[yw * kFLdG + xq], g11 = sG[yw * kFLdG + yq];
-							const double h00 = cw * g00 - sw * g10, h01 = cw * g01 - sw * g11; // rows: T_w^T from the left
-							const double h10 = sw * g00 + cw * g10, h11 = sw * g01 + cw * g11;
-							sG[xw * kFLdG + xq] = cq * h00 - sq * h01; // columns: T_q from the right
-							sG[xw * kFLdG + yq] = sq * h00 + cq * h01;
-							sG[yw * kFLdG + xq] = cq * h10 - sq * h11;
-							sG[yw * kFLdG + yq] = sq * h10 + cq * h11;
+							g0[xq] = cq * h00 - sq * h01; // columns: T_q from the right
+							g0[yq] = sq * h00 + cq * h01;
+							g1[xq] = cq * h10 - sq * h11;
+							g1[yq] = sq * h10 + cq * h11;
 						}
 						if (sq != 0.0)
 						{
-#pragma unroll
-							for (int h = 0; h < 2; ++h)
-							{
-								const int r = 2 * bw + h;
-								const double jx = sJ[r * kFLdG + xq], jy = sJ[r * kFLdG + yq];
-								sJ[r * kFLdG + xq] = cq * jx - sq * jy;
-								sJ[r * kFLdG + yq] = sq * jx + cq * jy;
-							}
+							j0[xq] = cq * a0x - sq * a0y;
+							j0[yq] = sq * a0x + cq * a0y;
+							j1[xq] = cq * a1x - sq * a1y;
+							j1[yq] = sq * a1x + cq * a1y;
 						}
 					}
 					__syncthreads();
@@ -959,6 +961,7 @@ __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 4
 			dbg[item_id * 8 + 2] = tq3 - tq2;
 			dbg[item_id * 8 + 3] = dbg_rounds;
 			dbg[item_id * 8 + 5] = tq4;
+			dbg[item_id * 8 + 6] = tqA;
 			tq4 = 0;
 		}
 	}
@@ -1710,10 +1713,22 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				QTB_CUDA(cudaMemsetAsync(L.d_off, 0, kMaxSweeps * sizeof(unsigned long long), ctx.stream));
 				if (!use_panel)
 				{
-					L.d_gpart = (double *)ctx_alloc(ctx, (size_t)L.max_items * L.nch_max * kPMax * kPMax * sizeof(double));
+					L.d_gpart = (double *)ctx_alloc(ctx, (size_t)L.max_items * std::max(L.nch_max * kPMax * kPMax, kFClusterMax * kFP * kFP) * sizeof(double));
 					L.d_rot = (double *)ctx_alloc(ctx, (size_t)L.max_items * kPMax * kPMax * sizeof(double));
 					L.d_flags = (int *)ctx_alloc(ctx, (size_t)L.max_items * sizeof(int));
 				}
+			}
+			// fused path: CTAs per pair, the largest power of two that keeps the busiest step within one wave of resident
+			// CTAs (4 per SM); more CTAs per pair shorten the Gram / update phases, a second wave doubles the step
+			int fused_cluster = 1;
+			if (use_fused)
+			{
+				static const int fc_env = std::getenv("QTB_SVD_FCLUSTER") ? std::atoi(std::getenv("QTB_SVD_FCLUSTER")) : 0;
+				const int resident = ctx.sm_count * 4 - ctx.sm_count / 4; // cluster placement never reaches the full count
+				while (fused_cluster < kFClusterMax && lanes[0].max_items * fused_cluster * 2 <= resident)
+					fused_cluster *= 2;
+				if (fc_env == 1 || fc_env == 2 || fc_env == 4 || fc_env == 8)
+					fused_cluster = fc_env;
 			}
 			// fork: the lanes start after everything enqueued so far on the context's stream (densify, uploads)
 			if (nlanes > 1)
@@ -1752,22 +1767,36 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 								d_dbg = (long long *)ctx_alloc(ctx, (size_t)cnt * 8 * sizeof(long long));
 								QTB_CUDA(cudaMemsetAsync(d_dbg, 0, (size_t)cnt * 8 * sizeof(long long), L.stream));
 							}
-							svd_fused_kernel<<<cnt * kFCluster, kFThreads, 0, L.stream>>>(d_groups, its, X, L.d_gpart, L.d_rot, L.d_flags,
-							                                                              L.d_off + sweep, conv_tol, fused_inner, inner_tol, d_dbg);
+							{
+								cudaLaunchConfig_t cfg = {};
+								cfg.gridDim = dim3((unsigned)(cnt * fused_cluster));
+								cfg.blockDim = dim3(kFThreads);
+								cfg.dynamicSmemBytes = 0;
+								cfg.stream = L.stream;
+								cudaLaunchAttribute at[1];
+								at[0].id = cudaLaunchAttributeClusterDimension;
+								at[0].val.clusterDim.x = (unsigned)fused_cluster;
+								at[0].val.clusterDim.y = 1;
+								at[0].val.clusterDim.z = 1;
+								cfg.attrs = at;
+								cfg.numAttrs = 1;
+								QTB_CUDA(cudaLaunchKernelEx(&cfg, svd_fused_kernel, (const SvdGroup *)d_groups, its, X, L.d_gpart, L.d_rot,
+								                            L.d_flags, L.d_off + sweep, conv_tol, fused_inner, inner_tol, d_dbg));
+							}
 							if (d_dbg)
 							{
 								std::vector<long long> h((size_t)cnt * 8);
 								QTB_CUDA(cudaMemcpyAsync(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, L.stream));
 								QTB_CUDA(cudaStreamSynchronize(L.stream));
-								double a[6] = {0, 0, 0, 0, 0, 0}, mx[6] = {0, 0, 0, 0, 0, 0};
+								double a[7] = {0, 0, 0, 0, 0, 0, 0}, mx[7] = {0, 0, 0, 0, 0, 0, 0};
 								for (int i = 0; i < cnt; ++i)
-									for (int k = 0; k < 6; ++k)
+									for (int k = 0; k < 7; ++k)
 									{
 										a[k] += (double)h[i * 8 + k] / cnt;
 										mx[k] = std::max(mx[k], (double)h[i * 8 + k]);
 									}
-								std::fprintf(stderr, "[qtb svd] fused phases (cycles, CTA 0 of %d clusters) sweep %d: gram+barrier avg %.0f max %.0f | eig avg %.0f max %.0f | barrier %.0f max %.0f | rounds avg %.1f max %.0f | update avg %.0f max %.0f | phase A total avg %.0f\n",
-								             cnt, sweep, a[0], mx[0], a[1], mx[1], a[2], mx[2], a[3], mx[3], a[4], mx[4], a[5]);
+								std::fprintf(stderr, "[qtb svd] fused phases (cycles, CTA 0 of %d clusters) sweep %d: gram+barrier avg %.0f max %.0f | eig avg %.0f max %.0f | barrier %.0f max %.0f | rounds avg %.1f max %.0f | update avg %.0f max %.0f | phase A total avg %.0f, with barrier %.0f\n",
+								             cnt, sweep, a[0], mx[0], a[1], mx[1], a[2], mx[2], a[3], mx[3], a[4], mx[4], a[5], a[6]);
 								ctx_free(ctx, d_dbg);
 							}
 							ctx.counters[0] += 1;
