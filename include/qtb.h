@@ -162,6 +162,38 @@ qtb_status qtb_mul_lastdim(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *
 qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncate, double tol, int64_t min_size,
                    int64_t max_size, double pow, qtb_tensor **u, qtb_tensor **d, qtb_tensor **v);
 
+/* truncate(U, d, V, max, min, tol, pow) / truncate(e, S, max, min, tol, pow) as free-standing operations (reference
+ * blockTensor/LinearAlgebra.h:244-247, btensor_linalg.cpp:657-755,768-803): `d` is rank 1 (one section per sector,
+ * descending inside a sector), `u` / `v` (either may be NULL) carry the sector as their last index. */
+qtb_status qtb_truncate(qtb_ctx *ctx, const qtb_tensor *u, const qtb_tensor *d, const qtb_tensor *v, int64_t max_size,
+                        int64_t min_size, double tol, double pow, qtb_tensor **u_out, qtb_tensor **d_out, qtb_tensor **v_out);
+/* eigh(A, split) / eigh(A, split, tol, min, max, pow) of a block-symmetric matrix (reference
+ * blockTensor/LinearAlgebra.h:159-192, btensor_linalg.cpp:294-389,816-829): A = U diag(e) U^T per charge group, e
+ * ascending inside a group, U orthonormal, output structure like d / U of the SVD. The reference's own implementation
+ * crashes (SIGSEGV) in the oracle build and its truncation moves the same tuple element twice (:789-790); the contract
+ * here is the mathematical one, with the truncation threshold taken over |e|. */
+qtb_status qtb_eigh(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncate, double tol, int64_t min_size,
+                    int64_t max_size, double pow, qtb_tensor **e, qtb_tensor **u);
+
+/* ---- structural reshapes (btensor::reshape(index_groups), btensor.cpp:2986-3024; btensor::reshape_as<mode>(other),
+ *      :3026-3083). Metadata only for packed blocks; strided views are gathered first. ------------------------------ */
+/* index_groups: the n_groups boundaries between the groups of consecutive dims that are merged (rank n_groups + 1 out) */
+qtb_status qtb_reshape(qtb_ctx *ctx, const qtb_tensor *a, int64_t n_groups, const int64_t *index_groups, qtb_tensor **out);
+/* overwrite_cvals = 0: reshape_mode::dims_only (keeps a's selection rule, checks the block fluxes);
+ *                  1: reshape_mode::overwrite_c_vals (takes `like`'s selection rule, checks every block against it) */
+qtb_status qtb_reshape_as(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *like, int overwrite_cvals, qtb_tensor **out);
+
+/* ---- generalised contraction D = alpha*C + beta*A.B (btensor::tensorgdot, declared at btensor.h:624-627 and never
+ *      defined in the reference; semantics of the dense tensorgdot, include/tensorgdot.h:22-86). When C has exactly the
+ *      block table of A.B the combination is the epilogue of the grouped GEMM. ------------------------------------- */
+qtb_status qtb_tensorgdot(qtb_ctx *ctx, const qtb_tensor *c, const qtb_tensor *a, const qtb_tensor *b, int64_t k,
+                          const int64_t *dims_a, const int64_t *dims_b, double beta, double alpha, qtb_tensor **out);
+
+/* ---- packed block tensor <-> file (structure, block table, arena image in one file; the
+ *      reference has no btensor serialisation) ---------------------------------------------------------------------- */
+qtb_status qtb_tensor_save(qtb_ctx *ctx, const qtb_tensor *t, const char *path);
+qtb_status qtb_tensor_load(qtb_ctx *ctx, const char *path, qtb_tensor **out);
+
 /* ---- two-site DMRG pieces (dmrg.cpp) ----------------------------------------------------------------------- */
 /* details::hamil2site_times_state, dmrg.cpp:520-531 */
 qtb_status qtb_heff_apply(qtb_ctx *ctx, const qtb_tensor *psi, const qtb_tensor *h2, const qtb_tensor *lenv,

@@ -633,6 +633,63 @@ def svd_trunc(t: BT, split: int, tol: float, min_size: int, max_size: int, pw: f
     return truncate(U, d, V, max_size, min_size, tol, pw)
 
 
+def reshape(t: BT, index_groups: Sequence[int]) -> BT:
+    """reference btensor::reshape(index_groups), sources/btensor.cpp:2986-3024 (helpers :2832-2985): consecutive dims
+    between the boundaries are merged; every combination of the merged sections becomes a section (row-major, last
+    index fastest) with size = product and charge = product; a block's new index is the flattened old one."""
+    r = t.rank
+    bounds = [0] + [int(x) for x in index_groups] + [r]
+    out_rank = len(bounds) - 1
+    sec_sizes, cvals = [], []
+    for g in range(out_rank):
+        dims = list(range(bounds[g], bounds[g + 1]))
+        ss, cv = [1], [q_neutral(t.nc)]
+        for d in dims:
+            ss = [a * b for a in ss for b in t.sec_sizes[d]]
+            cv = [q_op(a, b, t.mods) for a in cv for b in t.cvals[d]]
+        sec_sizes.append(ss)
+        cvals.append(cv)
+    out = BT(sec_sizes, cvals, t.sel, {}, t.mods)
+    for idx, blk in t.blocks.items():
+        new = []
+        for g in range(out_rank):
+            f = 0
+            for d in range(bounds[g], bounds[g + 1]):
+                f = f * t.nsec[d] + idx[d]
+            new.append(f)
+        shape = [int(np.prod(blk.shape[bounds[g]:bounds[g + 1]], dtype=np.int64)) for g in range(out_rank)]
+        out.blocks[tuple(new)] = np.ascontiguousarray(blk).reshape(shape)
+    return out
+
+
+def tensorgdot(c: BT, a: BT, b: BT, dims_a: Sequence[int], dims_b: Sequence[int], beta: float = 1.0, alpha: float = 1.0) -> BT:
+    """D = alpha*C + beta*A.B: btensor::tensorgdot is declared (reference include/blockTensor/btensor.h:624-627) and never
+    defined; semantics of the dense routine, include/tensorgdot.h:22-86 (argument order add, mul1, mul2, dims1, dims2,
+    beta, alpha). Block list = union of C's and (A.B)'s."""
+    t = tensordot(a, b, dims_a, dims_b)
+    out = c.structure_like()
+    for k in sorted(set(c.blocks) | set(t.blocks)):
+        v = 0.0
+        if k in c.blocks:
+            v = v + alpha * c.blocks[k]
+        if k in t.blocks:
+            v = v + beta * t.blocks[k]
+        out.blocks[k] = v
+    return out
+
+
+def eigh_groups(t: BT, split: int):
+    """Mathematical oracle for eigh(btensor, split) (reference blockTensor/LinearAlgebra.h:159-192, btensor_linalg.cpp:
+    294-389 — the reference's own implementation crashes in the oracle build, see ref_harness eigh): numpy.linalg.eigh of
+    every densified charge group of the rank-2 reshape, groups in the order of svd_groups. Returns [(e ascending, U)]"""
+    m = reshape_split(t, split)
+    out = []
+    for dense, rows, cols in svd_groups(m):
+        e, u = np.linalg.eigh((dense + dense.T) / 2)
+        out.append((e, u, rows, cols))
+    return out
+
+
 def recompose(U: BT, d: BT, V: BT) -> BT:
     """U * d * V^T contracted over the bond: the gauge-independent quantity SVD parity is judged on."""
     Ud = mul_bcast(U, d)

@@ -427,6 +427,68 @@ qtb_status qtb_svd(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncat
 	    });
 }
 
+qtb_status qtb_eigh(qtb_ctx *ctx, const qtb_tensor *a, int64_t split, int truncate, double tol, int64_t min_size,
+                    int64_t max_size, double pow, qtb_tensor **e, qtb_tensor **u)
+{
+	return guarded(ctx,
+	    [&]()
+	    {
+		    std::unique_ptr<Tensor> te, tu;
+		    block_eigh(ctx->c, *a->t, split, truncate != 0, tol, min_size, max_size, pow, te, tu);
+		    *e = wrap(std::move(te));
+		    *u = wrap(std::move(tu));
+	    });
+}
+qtb_status qtb_truncate(qtb_ctx *ctx, const qtb_tensor *u, const qtb_tensor *d, const qtb_tensor *v, int64_t max_size,
+                        int64_t min_size, double tol, double pow, qtb_tensor **u_out, qtb_tensor **d_out, qtb_tensor **v_out)
+{
+	return guarded(ctx,
+	    [&]()
+	    {
+		    QTB_REQUIRE(d != nullptr && d_out != nullptr, QTB_ERR_INVALID_ARGUMENT, "truncate: d is required");
+		    std::vector<const Tensor *> units;
+		    if (u)
+			    units.push_back(u->t.get());
+		    if (v)
+			    units.push_back(v->t.get());
+		    std::unique_ptr<Tensor> td;
+		    std::vector<std::unique_ptr<Tensor>> outs;
+		    block_truncate(ctx->c, *d->t, units, tol, min_size, max_size, pow, td, outs);
+		    *d_out = wrap(std::move(td));
+		    size_t k = 0;
+		    if (u)
+			    *u_out = wrap(std::move(outs[k++]));
+		    if (v)
+			    *v_out = wrap(std::move(outs[k++]));
+	    });
+}
+qtb_status qtb_reshape(qtb_ctx *ctx, const qtb_tensor *a, int64_t n_groups, const int64_t *index_groups, qtb_tensor **out)
+{
+	return guarded(ctx, [&]() { *out = wrap(reshape(ctx->c, *a->t, std::vector<i64>(index_groups, index_groups + n_groups))); });
+}
+qtb_status qtb_reshape_as(qtb_ctx *ctx, const qtb_tensor *a, const qtb_tensor *like, int overwrite_cvals, qtb_tensor **out)
+{
+	return guarded(ctx, [&]() { *out = wrap(reshape_as(ctx->c, *a->t, *like->t, overwrite_cvals != 0)); });
+}
+qtb_status qtb_tensorgdot(qtb_ctx *ctx, const qtb_tensor *c, const qtb_tensor *a, const qtb_tensor *b, int64_t k,
+                          const int64_t *dims_a, const int64_t *dims_b, double beta, double alpha, qtb_tensor **out)
+{
+	return guarded(ctx,
+	    [&]()
+	    {
+		    *out = wrap(tensorgdot(ctx->c, *c->t, *a->t, *b->t, std::vector<i64>(dims_a, dims_a + k),
+		                           std::vector<i64>(dims_b, dims_b + k), beta, alpha));
+	    });
+}
+qtb_status qtb_tensor_save(qtb_ctx *ctx, const qtb_tensor *t, const char *path)
+{
+	return guarded(ctx, [&]() { save_tensor(ctx->c, *t->t, path); });
+}
+qtb_status qtb_tensor_load(qtb_ctx *ctx, const char *path, qtb_tensor **out)
+{
+	return guarded(ctx, [&]() { *out = wrap(load_tensor(ctx->c, path)); });
+}
+
 qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce_fn allreduce, void *user)
 {
 	return guarded(ctx, 

@@ -300,8 +300,10 @@ void download(Ctx &ctx, const Tensor &t, double *host_out);
 std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t); // packed copy (gathers strided views)
 
 // kernels (qtb_gemm.cu / qtb_vec.cu)
+// cin != nullptr: c = alpha * cin + beta * (a . b), cin laid out like the output (the tensorgdot epilogue)
 void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
-                         const Plan::Owned *owned = nullptr);
+                         const Plan::Owned *owned = nullptr, const double *cin = nullptr, double alpha = 0.0,
+                         double beta = 1.0);
 // static tile schedule: longest-processing-time-first assignment of the cost-modelled tiles to `ncta` CTAs; reorders
 // `tiles`/`cost` so that the tiles of one CTA are contiguous (heaviest first) and returns cta_begin[ncta + 1]
 std::vector<int32_t> schedule_tiles(std::vector<GemmTile> &tiles, std::vector<double> &cost, int ncta);

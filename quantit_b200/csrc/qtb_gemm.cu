@@ -208,7 +208,8 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
     grouped_gemm_kernel(const GemmTile *__restrict__ tiles, const int32_t *__restrict__ cta_begin,
                         const GemmPair *__restrict__ pairs, const int32_t *__restrict__ offpool,
-                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C, int bulk_mask)
+                        const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C, int bulk_mask,
+                        const double *__restrict__ Cin, double alpha, double beta)
 {
 	constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
 	constexpr int PAD = Cfg::kPad;
@@ -485,6 +486,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 						{
 							const int n = n0 + wn0 + j * 8 + 2 * q;
 							double *dst = Cb + (size_t)m * N + n;
+							if (Cin != nullptr)
+							{ // tensorgdot epilogue: D = alpha C + beta A.B (C has the output's packed layout)
+								const double *src = Cin + ob.c_off + (size_t)m * N + n;
+								if (n < N)
+									acc[i][j][0] = alpha * src[0] + beta * acc[i][j][0];
+								if (n + 1 < N)
+									acc[i][j][1] = alpha * src[1] + beta * acc[i][j][1];
+							}
 							if (n + 1 < N)
 							{
 								if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)
@@ -602,7 +611,8 @@ using Cfg128 = GemmCfg<128, 128, 16, 64, 32, 4, 1, true>; // 8 consumer warps + 
 
 template <class Cfg>
 static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, const double *b, double *c,
-                       const GemmTile *d_tiles, const int32_t *d_cta_begin, int ncta)
+                       const GemmTile *d_tiles, const int32_t *d_cta_begin, int ncta, const double *cin, double alpha,
+                       double beta)
 {
 	auto kern = grouped_gemm_kernel<Cfg>;
 	if (ctx.attr_once(which)) // per context (= per device): the opt-in to > 48 KB of dynamic shared memory
@@ -611,12 +621,12 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 	// aligned (always for the engine's own arenas; adopted blocks may not be)
 	const int bulk_mask = ~0 ^ ((reinterpret_cast<uintptr_t>(a) & 15) ? 1 : 0) ^ ((reinterpret_cast<uintptr_t>(b) & 15) ? 2 : 0);
 	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_pairs,
-	                                                            plan.d_offpool, a, b, c, bulk_mask);
+	                                                            plan.d_offpool, a, b, c, bulk_mask, cin, alpha, beta);
 	QTB_CUDA(cudaGetLastError());
 }
 
 void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
-                         const Plan::Owned *owned)
+                         const Plan::Owned *owned, const double *cin, double alpha, double beta)
 {
 	const GemmTile *d_tiles = owned ? owned->d_tiles : plan.d_tiles;
 	const int32_t *d_cta_begin = owned ? owned->d_cta_begin : plan.d_cta_begin;
@@ -624,6 +634,8 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 	const int ncta = owned ? owned->ncta : plan.ncta;
 	if (ntiles == 0)
 		return;
+	QTB_REQUIRE(cin == nullptr || plan.tile_cfg != 2, QTB_ERR_INVALID_ARGUMENT,
+	            "the fused linear-combination epilogue is not available on the streaming (MPO) kernel");
 	if (plan.tile_cfg == 2)
 	{
 		const int grid = std::min(ntiles, ctx.sm_count * 8);
@@ -635,9 +647,9 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 		QTB_CUDA(cudaGetLastError());
 	}
 	else if (plan.tile_cfg == 0)
-		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c, d_tiles, d_cta_begin, ncta);
+		launch_cfg<Cfg64>(ctx, 0, plan, a, b, c, d_tiles, d_cta_begin, ncta, cin, alpha, beta);
 	else
-		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c, d_tiles, d_cta_begin, ncta);
+		launch_cfg<Cfg128>(ctx, 1, plan, a, b, c, d_tiles, d_cta_begin, ncta, cin, alpha, beta);
 	ctx.counters[0] += 1;
 	ctx.counters[1] += 1;
 	ctx.counters[6] += owned ? owned->flops : plan.flops;

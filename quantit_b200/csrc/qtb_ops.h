@@ -27,6 +27,17 @@ std::unique_ptr<Tensor> two_sites_update(Ctx &ctx, const Tensor &psi, const Tens
 // qtb_svd.cu
 void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size,
                double pow, std::unique_ptr<Tensor> &u, std::unique_ptr<Tensor> &d, std::unique_ptr<Tensor> &v);
+void block_eigh(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pow,
+                std::unique_ptr<Tensor> &e, std::unique_ptr<Tensor> &u);
+void block_truncate(Ctx &ctx, const Tensor &d, const std::vector<const Tensor *> &units, double tol, i64 min_size, i64 max_size,
+                    double pow, std::unique_ptr<Tensor> &d_out, std::vector<std::unique_ptr<Tensor>> &units_out);
+// qtb_shape.cpp
+std::unique_ptr<Tensor> reshape(Ctx &ctx, const Tensor &a, const std::vector<i64> &index_groups);
+std::unique_ptr<Tensor> reshape_as(Ctx &ctx, const Tensor &a, const Tensor &like, bool overwrite_cvals);
+std::unique_ptr<Tensor> tensorgdot(Ctx &ctx, const Tensor &c, const Tensor &a, const Tensor &b, const std::vector<i64> &da,
+                                   const std::vector<i64> &db, double beta, double alpha);
+void save_tensor(Ctx &ctx, const Tensor &t, const char *path);
+std::unique_ptr<Tensor> load_tensor(Ctx &ctx, const char *path);
 // qtb_dmrg.cpp
 // <a|obs|b> (obs != nullptr) or <a|b>: reference contract(bMPS, bMPS[, bMPO]), sources/MPT.cpp:211-233, 275-292
 double contract(Ctx &ctx, i64 L, const Tensor *const *a, const Tensor *const *b, const Tensor *const *obs);

@@ -1200,6 +1200,92 @@ __global__ void svd_scatter_kernel(const ScatterDesc *__restrict__ descs, int nd
 	}
 }
 
+// ---- eigh support: Frobenius norm of every group's dense matrix, the diagonal shift ---------------------------------
+struct EighMat
+{
+	i64 base;
+	int ld, m, n;
+};
+struct EighDiag
+{
+	i64 pos0; // element (row_off, col_off) of the section's diagonal block
+	int ld, size, group;
+};
+__global__ void __launch_bounds__(256) eigh_fro_kernel(const EighMat *__restrict__ mats, const double *__restrict__ X,
+                                                        double *__restrict__ partial)
+{
+	__shared__ double sh[8];
+	const EighMat M = mats[blockIdx.y];
+	double acc = 0.0;
+	for (int c = blockIdx.x; c < M.n; c += gridDim.x)
+		for (int r = threadIdx.x; r < M.m; r += 256)
+		{
+			const double v = X[M.base + (i64)c * M.ld + r];
+			acc += v * v;
+		}
+	for (int o = 16; o > 0; o >>= 1)
+		acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0)
+		sh[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		double t = 0.0;
+		for (int w = 0; w < 8; ++w)
+			t += sh[w];
+		partial[(size_t)blockIdx.y * 64 + blockIdx.x] = t;
+	}
+}
+__global__ void eigh_shift_value_kernel(const double *__restrict__ partial, double *__restrict__ shift)
+{ // fixed summation order: reproducible
+	if (threadIdx.x == 0)
+	{
+		double t = 0.0;
+		for (int k = 0; k < 64; ++k)
+			t += partial[(size_t)blockIdx.x * 64 + k];
+		shift[blockIdx.x] = sqrt(t) * (1.0 + 1e-9);
+	}
+}
+__global__ void eigh_add_diag_kernel(const EighDiag *__restrict__ descs, const double *__restrict__ shift, double *__restrict__ X)
+{
+	const EighDiag d = descs[blockIdx.x];
+	const double c = shift[d.group];
+	for (int i = threadIdx.x; i < d.size; i += blockDim.x)
+		X[d.pos0 + (i64)i * (d.ld + 1)] += c;
+}
+
+// Rayleigh quotients e_j = u_j^T (A u_j) of the kept eigenvectors of one charge group: U and W = A.U blocks are packed
+// [rows, kept] row-major; one CTA per group, a thread per column, blocks and rows in a fixed order (reproducible).
+struct RayleighBlock
+{
+	i64 u_off, w_off;
+	int rows, pad_;
+};
+struct RayleighGroup
+{
+	i64 e_off;
+	int kept, blk_begin, blk_end, pad_;
+};
+__global__ void __launch_bounds__(256) eigh_rayleigh_kernel(const RayleighGroup *__restrict__ groups,
+                                                             const RayleighBlock *__restrict__ blocks,
+                                                             const double *__restrict__ U, const double *__restrict__ W,
+                                                             double *__restrict__ E)
+{
+	const RayleighGroup G = groups[blockIdx.x];
+	for (int j = threadIdx.x; j < G.kept; j += 256)
+	{
+		double acc = 0.0;
+		for (int b = G.blk_begin; b < G.blk_end; ++b)
+		{
+			const RayleighBlock B = blocks[b];
+			const double *u = U + B.u_off + j, *w = W + B.w_off + j;
+			for (int r = 0; r < B.rows; ++r)
+				acc += u[(i64)r * G.kept] * w[(i64)r * G.kept];
+		}
+		E[G.e_off + j] = acc;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1254,9 +1340,13 @@ static std::vector<i64> remove_unit_blocks(const std::vector<i64> &last_index_of
 
 } // namespace
 
-void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pw,
-               std::unique_ptr<Tensor> &U, std::unique_ptr<Tensor> &D, std::unique_ptr<Tensor> &V)
+// mode 0: singular value decomposition. mode 1: eigen-decomposition of a block-symmetric matrix (block_eigh below): every
+// charge group is shifted by c = ||A_g||_F on its diagonal, which makes it positive semi-definite, so that its SVD is
+// its eigen-decomposition (sigma = e + c, U = eigenvectors); D receives the eigenvalues in ascending order, V is not built.
+static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pw,
+                           std::unique_ptr<Tensor> &U, std::unique_ptr<Tensor> &D, std::unique_ptr<Tensor> &V, int mode)
 {
+	const bool eigh_mode = mode == 1;
 	const i64 r = a.st.rank, nc = a.st.ct.nc;
 	QTB_REQUIRE(split >= 0 && split <= r, QTB_ERR_INVALID_ARGUMENT, "svd: split outside [0, rank]");
 	QTB_REQUIRE(r <= 8, QTB_ERR_INVALID_ARGUMENT, "svd: rank > 8 is not supported");
@@ -1346,6 +1436,18 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		g.col_sec0 = g.cols[0].first;
 	}
 	const i64 ng = (i64)groups.size();
+	if (eigh_mode)
+	{ // block-square: the row sections of a group are its column sections, with the same sizes
+		QTB_REQUIRE(n_row_sec == n_col_sec, QTB_ERR_INVALID_ARGUMENT, "eigh: the row and column legs have different section counts");
+		for (auto &g : groups)
+		{
+			bool ok = g.m == g.n && g.rows.size() == g.cols.size();
+			for (size_t i = 0; ok && i < g.rows.size(); ++i)
+				ok = g.rows[i].first == g.cols[i].first; // both ascending in the section index
+			QTB_REQUIRE(ok, QTB_ERR_INVALID_ARGUMENT, "eigh: a charge group of the matrix is not square (row sections differ from column sections)");
+			g.transposed = false;
+		}
+	}
 	// charge-sector sharding (qtb_ctx_set_sharding): every rank factorises the groups it owns (balanced by n^2 (m+n)),
 	// the singular values and the U / V arenas are made whole by allreduces of otherwise-zero buffers (exact).
 	std::vector<int32_t> g_owner(ng, 0);
@@ -1449,7 +1551,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			xtotal += 32 * n;
 		}
 	}
-	std::vector<double> sigma(sig_total, 0.0);
+	std::vector<double> sigma(sig_total, 0.0), eigh_shift;
 	std::vector<int> perm(sig_total, 0);
 	double *X = nullptr;
 	SvdGroup *d_groups = nullptr;
@@ -1505,6 +1607,45 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 			QTB_CUDA(cudaGetLastError());
 			ctx_free(ctx, d_dd);
 			ctx.counters[0] += 1;
+		}
+		// ---- eigh: A_g += ||A_g||_F I (positive semi-definite: the SVD below is then the eigen-decomposition) ----
+		double *d_shift = nullptr;
+		if (eigh_mode)
+		{
+			std::vector<EighDiag> ed;
+			std::vector<EighMat> em(ng);
+			for (i64 g = 0; g < ng; ++g)
+			{
+				const i64 base = use_qr ? qg[g].a_off : dg[g].x_off, ld = use_qr ? fm[g] : dg[g].ld;
+				em[g] = {base, (int)ld, (int)fm[g], dg[g].n};
+				if (!mine(g))
+					continue;
+				for (size_t i = 0; i < groups[g].rows.size(); ++i)
+				{
+					const i64 sec = groups[g].rows[i].first, ro = groups[g].rows[i].second, co = groups[g].cols[i].second;
+					i64 size = 1; // size of the flattened row section = number of rows of any of its blocks
+					for (i64 b : groups[g].blocks)
+						if (info[b].rs == sec)
+						{
+							size = info[b].rows;
+							break;
+						}
+					ed.push_back({base + ro + co * ld, (int)ld, (int)size, (int)g});
+				}
+			}
+			d_shift = (double *)ctx_alloc(ctx, (size_t)ng * (1 + 64) * sizeof(double));
+			auto d_em = (EighMat *)ctx_upload(ctx, em.data(), em.size() * sizeof(EighMat));
+			eigh_fro_kernel<<<dim3(64, (unsigned)ng), 256, 0, ctx.stream>>>(d_em, X, d_shift + ng);
+			eigh_shift_value_kernel<<<(unsigned)ng, 64, 0, ctx.stream>>>(d_shift + ng, d_shift);
+			if (!ed.empty())
+			{
+				auto d_ed = (EighDiag *)ctx_upload(ctx, ed.data(), ed.size() * sizeof(EighDiag));
+				eigh_add_diag_kernel<<<(unsigned)ed.size(), 128, 0, ctx.stream>>>(d_ed, d_shift, X);
+				ctx_free(ctx, d_ed);
+			}
+			QTB_CUDA(cudaGetLastError());
+			ctx_free(ctx, d_em);
+			ctx.counters[0] += 3;
 		}
 		// ---- QR preconditioning: F = Q R (blocked Householder), X = [R^T ; I] ----
 		std::vector<i64> qr_order;
@@ -1909,7 +2050,14 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 				ctx_free(ctx, d_qr);
 			}
 			QTB_CUDA(cudaMemcpyAsync(sigma.data(), d_sigma, sig_total * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+			if (eigh_mode)
+			{
+				eigh_shift.assign(ng, 0.0);
+				QTB_CUDA(cudaMemcpyAsync(eigh_shift.data(), d_shift, ng * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+			}
 			QTB_CUDA(cudaStreamSynchronize(ctx.stream));
+			if (d_shift)
+				ctx_free(ctx, d_shift);
 			ctx.counters[5] += sig_total * (i64)sizeof(double);
 		}
 	}
@@ -1931,13 +2079,21 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		std::fprintf(stderr, "[qtb svd] census: %ld values in %ld groups (largest n %ld), > 1e-6: %ld, > 1e-10: %ld, > 1e-14: %ld, > 1e-16: %ld of max %.3e; qr %d\n",
 		             (long)sig_total, (long)ng, nmax, c6, c10, c14, c16, smax, (int)use_qr);
 	}
-	// per group: permutation sorting sigma descending (LAPACK's order)
+	// per group: permutation sorting sigma descending (LAPACK's order); eigenvalues e = sigma - shift ascending
+	std::vector<double> dval(sigma); // what goes into D, per column of the workspace
 	for (i64 g = 0; g < ng; ++g)
 	{
 		int *p = perm.data() + sig_off[g];
 		std::iota(p, p + dg[g].n, 0);
 		const double *s = sigma.data() + sig_off[g];
-		std::stable_sort(p, p + dg[g].n, [&](int x, int y) { return s[x] > s[y]; });
+		if (eigh_mode)
+		{
+			for (int j = 0; j < dg[g].n; ++j)
+				dval[sig_off[g] + j] = s[j] - eigh_shift[g];
+			std::stable_sort(p, p + dg[g].n, [&](int x, int y) { return s[x] < s[y]; });
+		}
+		else
+			std::stable_sort(p, p + dg[g].n, [&](int x, int y) { return s[x] > s[y]; });
 	}
 
 	// ---- truncation (reference truncate_impl, btensor_linalg.cpp:657-755), on the host copy of the singular values ----
@@ -1964,7 +2120,39 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	std::vector<i64> u_alive(ub.size()), v_alive(vb.size());
 	std::iota(u_alive.begin(), u_alive.end(), 0);
 	std::iota(v_alive.begin(), v_alive.end(), 0);
-	if (truncate && sig_total > 0)
+	if (truncate && sig_total > 0 && eigh_mode)
+	{ // The reference's truncate(tuple<e, S>) (btensor_linalg.cpp:786-792) moves the same tuple element twice and assumes
+	  // descending values: it cannot work on eigenvalues. Corrected rule: the global threshold of compute_last_index is
+	  // taken over |e| (descending), every sector keeps its eigenpairs with |e| above it, in ascending order of e.
+		std::vector<double> vd;
+		for (i64 g = 0; g < ng; ++g)
+			for (int j = 0; j < dg[g].n; ++j)
+				vd.push_back(std::fabs(dval[sig_off[g] + j]));
+		std::sort(vd.begin(), vd.end(), std::greater<double>());
+		const i64 last = compute_last_index(vd, tol, pw, min_size, max_size);
+		QTB_REQUIRE(last >= 0, QTB_ERR_OUT_OF_RANGE, "truncate: index -1 is out of bounds (min_size = 0 with a full discard)");
+		double thr = vd[last];
+		thr -= 2 * thr * std::numeric_limits<double>::epsilon();
+		for (i64 g = 0; g < ng; ++g)
+		{
+			int *p = perm.data() + sig_off[g];
+			i64 n = 0;
+			for (int j = 0; j < dg[g].n; ++j)
+				if (std::fabs(dval[sig_off[g] + p[j]]) > thr)
+					p[n++] = p[j]; // stable: ascending e is preserved
+			kept[g] = n;
+			if (n == 0)
+			{ // an emptied sector loses its d block and every U block (its section size is retained, like the SVD case)
+				d_alive[g] = 0;
+				std::vector<i64> keep;
+				for (i64 pos : u_alive)
+					if (ub[pos].group != g)
+						keep.push_back(pos);
+				u_alive.swap(keep);
+			}
+		}
+	}
+	else if (truncate && sig_total > 0)
 	{
 		std::vector<double> vd;
 		vd.reserve(sig_total);
@@ -2016,7 +2204,7 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 		{
 			D->index.push_back(g);
 			for (i64 j = 0; j < kept[g]; ++j)
-				dvals.push_back(sigma[sig_off[g] + perm[sig_off[g] + j]]);
+				dvals.push_back(dval[sig_off[g] + perm[sig_off[g] + j]]);
 		}
 	D->nblocks = (i64)D->index.size();
 	D->dims.clear();
@@ -2142,13 +2330,203 @@ void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, 
 	};
 	std::vector<i64> neutral(nc, 0);
 	build(U, 0, split, false, a.st.sel, ub, u_alive, true);
-	build(V, split, r, true, neutral, vb, v_alive, false);
+	if (!eigh_mode)
+		build(V, split, r, true, neutral, vb, v_alive, false);
 	if (ng > 0)
 	{
 		ctx_free(ctx, X);
 		ctx_free(ctx, d_groups);
 		ctx_free(ctx, d_sigoff);
 		ctx_free(ctx, d_sigma);
+	}
+}
+
+void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pw,
+               std::unique_ptr<Tensor> &U, std::unique_ptr<Tensor> &D, std::unique_ptr<Tensor> &V)
+{
+	block_svd_impl(ctx, a, split, truncate, tol, min_size, max_size, pw, U, D, V, 0);
+}
+
+// eigh(btensor, split[, tol, min, max, pow]): reference blockTensor/LinearAlgebra.h:159-192, btensor_linalg.cpp:294-389,
+// 816-829. The reference implementation dies with SIGSEGV on every input tried when compiled here
+// so the contract here is the mathematical one: A = U diag(e) U^T per charge group,
+// U orthonormal, e ascending per group, output structure like the U / d of the SVD (bond charge = column charge).
+void block_eigh(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pw,
+                std::unique_ptr<Tensor> &E, std::unique_ptr<Tensor> &U)
+{
+	std::unique_ptr<Tensor> v_unused;
+	block_svd_impl(ctx, a, split, truncate, tol, min_size, max_size, pw, U, E, v_unused, 1);
+	// The diagonal shift costs absolute accuracy (the values come out to ~1e-14 sqrt(m) of the SHIFTED spectrum, and the
+	// safe shift ||A||_F can be 10-20x the spectral norm). The eigenvectors are good to that level, so their Rayleigh
+	// quotients e_j = u_j^T A u_j are good to its square: one extra contraction W = A.U and a column-wise dot.
+	const i64 r = a.st.rank, ur = U->st.rank;
+	if (U->nblocks == 0 || E->nblocks == 0)
+		return;
+	std::vector<i64> da, db;
+	for (i64 d = split; d < r; ++d)
+		da.push_back(d);
+	for (i64 d = 0; d < ur - 1; ++d)
+		db.push_back(d);
+	auto W = tensordot(ctx, a, *U, da, db);
+	std::vector<RayleighBlock> rb;
+	std::vector<RayleighGroup> rg;
+	for (i64 eb = 0; eb < E->nblocks; ++eb)
+	{
+		const i64 g = E->idx(eb)[0];
+		RayleighGroup G{};
+		G.e_off = E->offs[eb];
+		G.kept = (int)E->dm(eb)[0];
+		G.blk_begin = (int)rb.size();
+		for (i64 b = 0; b < U->nblocks; ++b)
+			if (U->idx(b)[ur - 1] == g)
+			{
+				const i64 wb = W->find_block(U->idx(b));
+				if (wb < 0)
+					continue; // A maps nothing onto this row section: contributes zero
+				i64 rows = 1;
+				for (i64 d = 0; d < ur - 1; ++d)
+					rows *= U->dm(b)[d];
+				QTB_REQUIRE(W->block_numel(wb) == U->block_numel(b) && U->dm(b)[ur - 1] == G.kept, QTB_ERR_RUNTIME,
+				            "eigh: unexpected block shape in the Rayleigh refinement");
+				rb.push_back({U->offs[b], W->offs[wb], (int)rows, 0});
+			}
+		G.blk_end = (int)rb.size();
+		rg.push_back(G);
+	}
+	if (rb.empty())
+		return;
+	auto d_rb = (RayleighBlock *)ctx_upload(ctx, rb.data(), rb.size() * sizeof(RayleighBlock));
+	auto d_rg = (RayleighGroup *)ctx_upload(ctx, rg.data(), rg.size() * sizeof(RayleighGroup));
+	eigh_rayleigh_kernel<<<(unsigned)rg.size(), 256, 0, ctx.stream>>>(d_rg, d_rb, U->arena->ptr, W->arena->ptr, E->arena->ptr);
+	QTB_CUDA(cudaGetLastError());
+	ctx_free(ctx, d_rb);
+	ctx_free(ctx, d_rg);
+	ctx.counters[0] += 1;
+}
+
+// truncate(U, d, V, max, min, tol, pow) / truncate(e, S, ...) as free-standing operations: reference
+// blockTensor/LinearAlgebra.h:244-247, btensor_linalg.cpp:657-755 (truncate_impl), :768-803. `d` is rank 1 with one
+// section per sector and descending values inside a sector; every tensor of `units` carries the sector as its LAST index.
+// Same rules as inside block_svd: global threshold from compute_last_index, strict `>` per sector, an emptied sector
+// keeps its section size and loses its d block, and of a run of consecutive blocks of an emptied sector only every
+// other one is removed from the unitaries (the reference's observed removal loop).
+void block_truncate(Ctx &ctx, const Tensor &d, const std::vector<const Tensor *> &units, double tol, i64 min_size, i64 max_size,
+                    double pw, std::unique_ptr<Tensor> &d_out, std::vector<std::unique_ptr<Tensor>> &units_out)
+{
+	QTB_REQUIRE(d.st.rank == 1, QTB_ERR_INVALID_ARGUMENT, "truncate: d must be a rank-1 tensor");
+	const i64 ng = d.st.nsec[0];
+	for (const Tensor *u : units)
+		QTB_REQUIRE(u->st.rank >= 1 && u->st.nsec[u->st.rank - 1] == ng, QTB_ERR_INVALID_ARGUMENT,
+		            "truncate: the last index of every unitary must carry the sectors of d");
+	std::vector<double> vals((size_t)d.numel());
+	download(ctx, d, vals.data());
+	std::vector<i64> blk_of(ng, -1), voff(d.nblocks + 1, 0);
+	for (i64 b = 0; b < d.nblocks; ++b)
+	{
+		blk_of[d.idx(b)[0]] = b;
+		voff[b + 1] = voff[b] + d.block_numel(b);
+	}
+	QTB_REQUIRE(!vals.empty(), QTB_ERR_OUT_OF_RANGE, "truncate: d holds no value");
+	std::vector<double> vd(vals);
+	std::sort(vd.begin(), vd.end(), std::greater<double>());
+	const i64 last = compute_last_index(vd, tol, pw, min_size, max_size);
+	QTB_REQUIRE(last >= 0, QTB_ERR_OUT_OF_RANGE, "truncate: index -1 is out of bounds (min_size = 0 with a full discard)");
+	double thr = vd[last];
+	thr -= 2 * thr * std::numeric_limits<double>::epsilon();
+	std::vector<i64> kept(ng, 0);
+	std::vector<char> alive(ng, 0);
+	for (i64 g = 0; g < ng; ++g)
+		if (blk_of[g] >= 0)
+		{
+			const i64 b = blk_of[g], n = d.block_numel(b);
+			i64 k = 0;
+			while (k < n && vals[voff[b] + k] > thr)
+				++k;
+			kept[g] = k;
+			alive[g] = k > 0;
+		}
+	auto new_size = [&](i64 g) { return alive[g] ? kept[g] : d.st.size_of(0, g); };
+	// d'
+	{
+		d_out = std::make_unique<Tensor>();
+		d_out->st = d.st;
+		for (i64 g = 0; g < ng; ++g)
+			d_out->st.sec_sizes[g] = new_size(g);
+		std::vector<GatherDesc> gd;
+		std::vector<i64> src_blocks;
+		for (i64 b = 0; b < d.nblocks; ++b)
+			if (alive[d.idx(b)[0]])
+			{
+				d_out->index.push_back(d.idx(b)[0]);
+				src_blocks.push_back(b);
+			}
+		d_out->nblocks = (i64)src_blocks.size();
+		d_out->dims_from_structure();
+		const i64 total = d_out->layout_packed();
+		d_out->arena = std::make_shared<Arena>(&ctx, total);
+		for (i64 k = 0; k < d_out->nblocks; ++k)
+		{
+			GatherDesc g{};
+			g.src_off = d.offs[src_blocks[k]];
+			g.dst_off = d_out->offs[k];
+			g.numel = d_out->block_numel(k);
+			g.rank = 1;
+			g.dims[0] = g.numel;
+			g.strides[0] = d.sd(src_blocks[k])[0];
+			if (g.numel > 0)
+				gd.push_back(g);
+		}
+		launch_gather(ctx, gd, d.arena->ptr, d_out->arena->ptr);
+		d_out->compute_hash();
+	}
+	units_out.clear();
+	for (const Tensor *up : units)
+	{
+		const Tensor &u = *up;
+		const i64 r = u.st.rank;
+		std::vector<i64> lastidx(u.nblocks), live(u.nblocks);
+		for (i64 b = 0; b < u.nblocks; ++b)
+			lastidx[b] = u.idx(b)[r - 1];
+		std::iota(live.begin(), live.end(), 0);
+		for (i64 g = ng - 1; g >= 0; --g)
+			if (blk_of[g] >= 0 && !alive[g])
+				live = remove_unit_blocks(lastidx, g, live);
+		auto out = std::make_unique<Tensor>();
+		out->st = u.st;
+		for (i64 g = 0; g < ng; ++g)
+			out->st.sec_sizes[out->st.sec_off[r - 1] + g] = new_size(g);
+		out->nblocks = (i64)live.size();
+		for (i64 b : live)
+			out->index.insert(out->index.end(), u.idx(b), u.idx(b) + r);
+		out->dims_from_structure();
+		// a block that survived the removal loop although its sector was emptied keeps its full width
+		for (i64 k = 0; k < out->nblocks; ++k)
+		{
+			const i64 g = out->idx(k)[r - 1];
+			if (blk_of[g] >= 0 && !alive[g])
+				out->dims[k * r + r - 1] = u.dm(live[k])[r - 1];
+		}
+		const i64 total = out->layout_packed();
+		out->arena = std::make_shared<Arena>(&ctx, total);
+		std::vector<GatherDesc> gd;
+		for (i64 k = 0; k < out->nblocks; ++k)
+		{
+			GatherDesc g{};
+			g.src_off = u.offs[live[k]];
+			g.dst_off = out->offs[k];
+			g.numel = out->block_numel(k);
+			g.rank = (int)r;
+			for (i64 dd = 0; dd < r; ++dd)
+			{
+				g.dims[dd] = out->dm(k)[dd];
+				g.strides[dd] = u.sd(live[k])[dd];
+			}
+			if (g.numel > 0)
+				gd.push_back(g);
+		}
+		launch_gather(ctx, gd, u.arena->ptr, out->arena->ptr);
+		out->compute_hash();
+		units_out.push_back(std::move(out));
 	}
 }
 

@@ -104,6 +104,14 @@ _SIGS = [
     ("qtb_mul_lastdim", C.c_int, [vp, vp, vp, C.POINTER(vp)]),
     ("qtb_svd", C.c_int, [vp, vp, i64, C.c_int, C.c_double, i64, i64, C.c_double, C.POINTER(vp), C.POINTER(vp),
                           C.POINTER(vp)]),
+    ("qtb_truncate", C.c_int, [vp, vp, vp, vp, i64, i64, C.c_double, C.c_double, C.POINTER(vp), C.POINTER(vp),
+                               C.POINTER(vp)]),
+    ("qtb_eigh", C.c_int, [vp, vp, i64, C.c_int, C.c_double, i64, i64, C.c_double, C.POINTER(vp), C.POINTER(vp)]),
+    ("qtb_reshape", C.c_int, [vp, vp, i64, p_i64, C.POINTER(vp)]),
+    ("qtb_reshape_as", C.c_int, [vp, vp, vp, C.c_int, C.POINTER(vp)]),
+    ("qtb_tensorgdot", C.c_int, [vp, vp, vp, vp, i64, p_i64, p_i64, C.c_double, C.c_double, C.POINTER(vp)]),
+    ("qtb_tensor_save", C.c_int, [vp, vp, C.c_char_p]),
+    ("qtb_tensor_load", C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     ("qtb_heff_apply", C.c_int, [vp, vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_env_left", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_env_right", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
@@ -415,6 +423,39 @@ class BTensor:
         _check(self.ctx.lib.qtb_mul_lastdim(self.ctx.h, self.h, d.h, C.byref(h)))
         return BTensor(self.ctx, h)
 
+    def reshape(self, index_groups: Sequence[int]) -> "BTensor":
+        """reference btensor::reshape(index_groups), btensor.cpp:2986: merges the groups of consecutive dims delimited by
+        `index_groups` (e.g. [split] -> a rank-2 tensor)"""
+        g = _arr(index_groups)
+        h = vp()
+        _check(self.ctx.lib.qtb_reshape(self.ctx.h, self.h, len(g), _pi(g) if len(g) else None, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def reshape_as(self, like: "BTensor", overwrite_c_vals: bool = False) -> "BTensor":
+        """reference btensor::reshape_as<mode>(other), btensor.cpp:3026"""
+        h = vp()
+        _check(self.ctx.lib.qtb_reshape_as(self.ctx.h, self.h, like.h, 1 if overwrite_c_vals else 0, C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def tensorgdot(self, mul1: "BTensor", mul2: "BTensor", dims1, dims2, beta: float = 1.0, alpha: float = 1.0) -> "BTensor":
+        """alpha * self + beta * mul1.mul2 — btensor::tensorgdot as declared at reference btensor.h:624 (semantics of the
+        dense include/tensorgdot.h:22)"""
+        da, db = _arr(dims1), _arr(dims2)
+        h = vp()
+        _check(self.ctx.lib.qtb_tensorgdot(self.ctx.h, self.h, mul1.h, mul2.h, len(da), _pi(da), _pi(db), float(beta),
+                                           float(alpha), C.byref(h)))
+        return BTensor(self.ctx, h)
+
+    def save(self, path: str) -> None:
+        _check(self.ctx.lib.qtb_tensor_save(self.ctx.h, self.h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, ctx: Optional[Context] = None) -> "BTensor":
+        ctx = ctx or default_context()
+        h = vp()
+        _check(ctx.lib.qtb_tensor_load(ctx.h, str(path).encode(), C.byref(h)))
+        return cls(ctx, h)
+
 
 def tensordot(a: BTensor, b: BTensor, dims_a, dims_b) -> BTensor:
     """free function, reference btensor.h:1230"""
@@ -430,6 +471,27 @@ def svd(a: BTensor, split: int, tol: Optional[float] = None, min_size: int = 1, 
                              -1 if max_size is None else int(max_size), float(pow), C.byref(hu), C.byref(hd),
                              C.byref(hv)))
     return BTensor(a.ctx, hu), BTensor(a.ctx, hd), BTensor(a.ctx, hv)
+
+
+def eigh(a: BTensor, split: int, tol: Optional[float] = None, min_size: int = 1, max_size: Optional[int] = None,
+         pow: float = 1.0):
+    """reference quantit::eigh(btensor, split[, tol, min, max, pow]), blockTensor/LinearAlgebra.h:167-192: (e, U) with
+    A = U diag(e) U^T per charge group, e ascending inside a group"""
+    he, hu = vp(), vp()
+    trunc = tol is not None
+    _check(a.ctx.lib.qtb_eigh(a.ctx.h, a.h, int(split), 1 if trunc else 0, float(tol or 0.0), int(min_size),
+                              -1 if max_size is None else int(max_size), float(pow), C.byref(he), C.byref(hu)))
+    return BTensor(a.ctx, he), BTensor(a.ctx, hu)
+
+
+def truncate(U: Optional[BTensor], d: BTensor, V: Optional[BTensor], max_size: Optional[int], min_size: int, tol: float,
+             pow: float = 2.0):
+    """reference quantit::truncate(U, d, V, max, min, tol, pow), blockTensor/LinearAlgebra.h:244-247"""
+    hu, hd, hv = vp(), vp(), vp()
+    _check(d.ctx.lib.qtb_truncate(d.ctx.h, U.h if U is not None else None, d.h, V.h if V is not None else None,
+                                  -1 if max_size is None else int(max_size), int(min_size), float(tol), float(pow),
+                                  C.byref(hu), C.byref(hd), C.byref(hv)))
+    return (BTensor(d.ctx, hu) if U is not None else None, BTensor(d.ctx, hd), BTensor(d.ctx, hv) if V is not None else None)
 
 
 def hamil2site_times_state(state: BTensor, hamil: BTensor, lenv: BTensor, renv: BTensor) -> BTensor:
