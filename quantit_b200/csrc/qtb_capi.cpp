@@ -203,6 +203,7 @@ qtb_status qtb_tensor_adopt(qtb_ctx *ctx, int64_t rank, int64_t nc, const int64_
 			    base = 0;
 		    t->arena = std::make_shared<Arena>((double *)base);
 		    t->arena->ctx = &ctx->c;
+		    ctx->c.arenas.insert(t->arena.get()); // orphaned (not freed) if the context goes first
 		    t->strides.resize(nblocks * rank);
 		    t->offs.resize(nblocks);
 		    for (int64_t nb = 0; nb < nblocks; ++nb)

@@ -287,6 +287,35 @@ class BTensor:
                                          C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def adopt(cls, sec_sizes: Sequence[Sequence[int]], cvals: Sequence[Sequence[Tuple[int, ...]]], sel: Tuple[int, ...],
+              blocks: Dict[Tuple[int, ...], object], mods: Optional[Sequence[int]] = None,
+              ctx: Optional[Context] = None) -> "BTensor":
+        """Zero-copy wrap of blocks that already live on the device (qtb_tensor_adopt): every value of `blocks` is a
+        float64 CUDA array exposing data_ptr() / stride() / shape (a torch.Tensor, possibly a strided view — what a
+        quantit::btensor holds per block). The arrays are kept alive by the returned object; the memory is not owned."""
+        ctx = ctx or default_context()
+        rank, nc = len(sec_sizes), len(sel)
+        nsec = _arr([len(s) for s in sec_sizes])
+        ss = _arr([x for s in sec_sizes for x in s])
+        cv = _arr([c for cs in cvals for q in cs for c in q])
+        sl = _arr(sel)
+        md = _arr(mods) if mods is not None else None
+        keys = list(blocks.keys())
+        for k in keys:
+            want = tuple(sec_sizes[d][i] for d, i in enumerate(k))
+            if tuple(blocks[k].shape) != want:
+                raise InvalidArgument(f"block {k} has shape {tuple(blocks[k].shape)}, sections say {want}")
+        idx = _arr([i for k in keys for i in k])
+        strides = _arr([int(s) for k in keys for s in blocks[k].stride()])
+        ptrs = (vp * max(len(keys), 1))(*[int(blocks[k].data_ptr()) for k in keys])
+        h = vp()
+        _check(ctx.lib.qtb_tensor_adopt(ctx.h, rank, nc, _pi(md) if md is not None else None, _pi(nsec), _pi(ss), _pi(cv),
+                                        _pi(sl), len(keys), _pi(idx), ptrs, _pi(strides), C.byref(h)))
+        out = cls(ctx, h)
+        out._keepalive = [blocks[k] for k in keys]
+        return out
+
     # ---- structure queries ----------------------------------------------------------------------------------------
     def dim(self) -> int:
         return int(self.ctx.lib.qtb_tensor_rank(self.h))
