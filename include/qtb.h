@@ -74,6 +74,12 @@ qtb_status qtb_ctx_counters(qtb_ctx *ctx, int64_t out[8]);
  * that stream, or torch.distributed as quantit_b200/sharding.py does) and return 0 on success. */
 typedef int (*qtb_allreduce_fn)(void *user, double *device_ptr, int64_t n, void *cuda_stream);
 qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce_fn allreduce, void *user);
+/* The engine's own NCCL communicator (preferred over the callback: no host code on the data path). libnccl is bound
+ * at run time with dlopen (`libnccl_path` may be NULL: "libnccl.so.2" as already mapped by the process, e.g. by torch).
+ * Rank 0 obtains a 128-byte unique id, the host broadcasts it to every rank by any means, every rank then calls
+ * qtb_ctx_init_nccl (collective: ncclCommInitRank). Also sets rank / world like qtb_ctx_set_sharding. */
+qtb_status qtb_nccl_unique_id(const char *libnccl_path, char out[128]);
+qtb_status qtb_ctx_init_nccl(qtb_ctx *ctx, int rank, int world, const char unique_id[128], const char *libnccl_path);
 /* longest-processing-time-first assignment of n weighted sections to `world` ranks (pure host; deterministic: ties go
  * to the lower section index / lower rank). owner_out[n]. */
 qtb_status qtb_lpt_assign(int64_t n, const double *weights, int world, int32_t *owner_out);

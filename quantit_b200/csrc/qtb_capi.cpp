@@ -497,13 +497,21 @@ qtb_status qtb_ctx_set_sharding(qtb_ctx *ctx, int rank, int world, qtb_allreduce
 	    {
 		    QTB_REQUIRE(ctx != nullptr, QTB_ERR_INVALID_ARGUMENT, "null context");
 		    QTB_REQUIRE(world >= 1 && rank >= 0 && rank < world, QTB_ERR_INVALID_ARGUMENT, "rank outside [0, world)");
-		    QTB_REQUIRE(world == 1 || allreduce != nullptr, QTB_ERR_INVALID_ARGUMENT,
-		                "sharding over more than one rank needs an allreduce callback");
+		    QTB_REQUIRE(world == 1 || allreduce != nullptr || ctx->c.nccl_comm != nullptr, QTB_ERR_INVALID_ARGUMENT,
+		                "sharding over more than one rank needs an allreduce callback or qtb_ctx_init_nccl");
 		    ctx->c.rank = rank;
 		    ctx->c.world = world;
 		    ctx->c.allreduce_fn = allreduce;
 		    ctx->c.allreduce_user = user;
 	    });
+}
+qtb_status qtb_nccl_unique_id(const char *libnccl_path, char out[128])
+{
+	return guarded([&]() { nccl_unique_id(libnccl_path, out); });
+}
+qtb_status qtb_ctx_init_nccl(qtb_ctx *ctx, int rank, int world, const char unique_id[128], const char *libnccl_path)
+{
+	return guarded(ctx, [&]() { ctx_init_nccl(ctx->c, rank, world, unique_id, libnccl_path); });
 }
 qtb_status qtb_lpt_assign(int64_t n, const double *weights, int world, int32_t *owner_out)
 {

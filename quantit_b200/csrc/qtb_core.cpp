@@ -20,6 +20,7 @@ namespace qtb
 // =====================================================================================================================
 Ctx::~Ctx()
 {
+	ctx_destroy_nccl(*this);
 	plan_cache.clear();
 	trim_cache();
 	for (Arena *a : arenas) // tensors that outlive the context: their arenas are orphaned, the blocks released below
@@ -223,6 +224,11 @@ void Ctx::allreduce(double *ptr, i64 n)
 {
 	if (world <= 1 || n <= 0)
 		return;
+	if (nccl_allreduce(*this, ptr, n))
+	{
+		counters[0] += 1;
+		return;
+	}
 	QTB_REQUIRE(allreduce_fn != nullptr, QTB_ERR_RUNTIME, "sharding is enabled but no allreduce callback is registered");
 	const int rc = allreduce_fn(allreduce_user, ptr, n, (void *)stream);
 	QTB_REQUIRE(rc == 0, QTB_ERR_RUNTIME, "the allreduce callback failed with code " + std::to_string(rc));
@@ -315,12 +321,15 @@ void add_section_weights(const Plan &plan, i64 owner_dim, std::vector<double> &w
 		weights[o.idx(b)[owner_dim]] += (double)plan.out_flops[b] + 1.0; // +1: empty blocks still cost a tile visit
 }
 
-std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b,
-                                        i64 owner_dim, const std::vector<int32_t> &owner)
+static const Plan::Owned &owned_tiles(Ctx &ctx, const std::shared_ptr<Plan> &plan, i64 owner_dim,
+                                      const std::vector<int32_t> &owner, const std::vector<i64> *c_off)
 {
 	uint64_t h = mix64(0x51a7d, (uint64_t)owner_dim * 131 + (uint64_t)ctx.rank * 7 + (uint64_t)ctx.world);
 	for (auto r : owner)
 		h = mix64(h, (uint64_t)r + 3);
+	if (c_off)
+		for (auto v : *c_off)
+			h = mix64(h, (uint64_t)v + 11);
 	auto it = plan->owned.find(h);
 	if (it == plan->owned.end())
 	{
@@ -332,6 +341,8 @@ std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &p
 			if (owner[o.idx(plan->tiles[t].out_blk)[owner_dim]] == ctx.rank)
 			{
 				mine.push_back(plan->tiles[t]);
+				if (c_off) // the block is written somewhere else than the plan's own packed layout
+					mine.back().c_off = (*c_off)[plan->tiles[t].out_blk];
 				cost.push_back(plan->tile_cost[t]);
 			}
 		for (i64 ob = 0; ob < o.nblocks; ++ob)
@@ -351,13 +362,33 @@ std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &p
 		}
 		it = plan->owned.emplace(h, ow).first;
 	}
+	return it->second;
+}
+
+std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b,
+                                        i64 owner_dim, const std::vector<int32_t> &owner, bool zero_rest)
+{
+	const Plan::Owned &ow = owned_tiles(ctx, plan, owner_dim, owner, nullptr);
 	auto out = std::make_unique<Tensor>(plan->out_proto);
 	out->arena = std::make_shared<Arena>(&ctx, plan->out_numel);
-	if (plan->out_numel)
+	if (plan->out_numel && zero_rest)
 		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, plan->out_numel * sizeof(double), ctx.stream));
-	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr, out->arena->ptr,
-	                    &it->second);
+	else if (plan->out_numel)
+	{ // only the owned blocks that no pair writes
+		const Tensor &o = plan->out_proto;
+		for (i64 ob = 0; ob < o.nblocks; ++ob)
+			if (plan->outs[ob].pair_begin == plan->outs[ob].pair_end && owner[o.idx(ob)[owner_dim]] == ctx.rank && o.block_numel(ob) > 0)
+				QTB_CUDA(cudaMemsetAsync(out->arena->ptr + o.offs[ob], 0, o.block_numel(ob) * sizeof(double), ctx.stream));
+	}
+	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr, out->arena->ptr, &ow);
 	return out;
+}
+
+void tensordot_owned_into(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b, i64 owner_dim,
+                          const std::vector<int32_t> &owner, const std::vector<i64> &c_off, double *c_arena)
+{
+	const Plan::Owned &ow = owned_tiles(ctx, plan, owner_dim, owner, &c_off);
+	launch_grouped_gemm(ctx, *plan, a.arena ? a.arena->ptr : nullptr, b.arena ? b.arena->ptr : nullptr, c_arena, &ow);
 }
 
 // =====================================================================================================================

@@ -282,8 +282,22 @@ struct Ctx
 	qtb_allreduce_fn allreduce_fn = nullptr;
 	void *allreduce_user = nullptr;
 	void allreduce(double *ptr, i64 n); // in-place sum over ranks, stream ordered; no-op when world == 1
+	void *nccl_comm = nullptr;          // the engine's own communicator (qtb_ctx_init_nccl): preferred over the callback
 	~Ctx();
 };
+
+// ---- NCCL bound at run time (qtb_nccl.cpp) ----------------------------------------------------------------------------
+struct OwnedRange
+{
+	i64 off, n; // element range of an arena
+	int owner;  // rank that computed it
+};
+void nccl_unique_id(const char *libpath, char out[128]);
+void ctx_init_nccl(Ctx &ctx, int rank, int world, const char id_bytes[128], const char *libpath);
+void ctx_destroy_nccl(Ctx &ctx);
+bool nccl_allreduce(Ctx &ctx, double *ptr, i64 n);
+bool nccl_exchange_ranges(Ctx &ctx, double *base, const std::vector<OwnedRange> &ranges);
+bool nccl_allgather(Ctx &ctx, double *base, i64 chunk);
 
 // ---- ops (host orchestration; kernels in the .cu files) --------------------------------------------------------------
 std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a,
@@ -312,8 +326,14 @@ int gemm_grid_limit(const Ctx &ctx, int tile_cfg); // CTAs the grouped GEMM keep
 std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world);
 // one step of a sharded chain of contractions: computes only the output blocks whose section along `owner_dim` belongs
 // to this rank (the rest of the freshly allocated arena is zero); `owner` maps sections of that dim to ranks.
+// zero_rest: clear the whole output arena first (needed when the result is summed over the ranks; an intermediate of a
+// chain that is only read through the blocks this rank owns does not need it — owned blocks without any matched pair
+// are cleared individually)
 std::unique_ptr<Tensor> tensordot_owned(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b,
-                                        i64 owner_dim, const std::vector<int32_t> &owner);
+                                        i64 owner_dim, const std::vector<int32_t> &owner, bool zero_rest = true);
+// same, writing every owned output block at c_off[block] of an existing arena (the caller's layout, not the plan's)
+void tensordot_owned_into(Ctx &ctx, const std::shared_ptr<Plan> &plan, const Tensor &a, const Tensor &b, i64 owner_dim,
+                          const std::vector<int32_t> &owner, const std::vector<i64> &c_off, double *c_arena);
 // a chain of contractions sharing one owner leg: accumulates the planner's flops per section of that leg
 void add_section_weights(const Plan &plan, i64 owner_dim, std::vector<double> &weights);
 void launch_gather_blocks(Ctx &ctx, const Tensor &src, double *dst_packed, const std::vector<i64> &dst_offs);

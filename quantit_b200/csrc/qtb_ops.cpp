@@ -6,6 +6,8 @@
 //   hamil2site_times_state         sources/dmrg.cpp:520-531
 //   compute_left_env/right_env     sources/dmrg.cpp:424-493
 //   one_step_lanczos, eig2x2Mat, two_sites_update   sources/dmrg.cpp:543-651
+#include <cstdlib>
+
 #include "qtb_ops.h"
 
 #include <algorithm>
@@ -201,6 +203,109 @@ struct ChainStep
 	std::vector<i64> da, db;
 	i64 owner_dim; // position of the carried leg in this step's output
 };
+
+// Second-level split of the carried leg ("split the largest sectors' GEMMs along M"): a view of `t`
+// whose sections along `dim` larger than 2 * piece are cut into pieces of `piece` rows (same charge). Metadata only:
+// every block becomes several blocks that address row ranges of the same memory. parent / start give, for every refined
+// section, the section it came from and its first row inside it.
+struct Refined
+{
+	std::unique_ptr<Tensor> t;
+	std::vector<i64> parent, start;
+};
+Refined refine_leg(const Tensor &t, i64 dim, i64 piece)
+{
+	Refined out;
+	const i64 r = t.st.rank, nc = t.st.ct.nc;
+	std::vector<i64> first_sub(t.st.nsec[dim] + 1, 0);
+	std::vector<i64> sizes;
+	for (i64 s = 0; s < t.st.nsec[dim]; ++s)
+	{
+		const i64 n = t.st.size_of(dim, s);
+		first_sub[s] = (i64)sizes.size();
+		if (n >= 2 * piece)
+			for (i64 r0 = 0; r0 < n; r0 += piece)
+			{
+				out.parent.push_back(s);
+				out.start.push_back(r0);
+				sizes.push_back(std::min(piece, n - r0));
+			}
+		else
+		{
+			out.parent.push_back(s);
+			out.start.push_back(0);
+			sizes.push_back(n);
+		}
+	}
+	first_sub[t.st.nsec[dim]] = (i64)sizes.size();
+	auto v = std::make_unique<Tensor>();
+	v->st.rank = r;
+	v->st.ct = t.st.ct;
+	v->st.sel = t.st.sel;
+	for (i64 d = 0; d < r; ++d)
+	{
+		if (d != dim)
+		{
+			v->st.nsec.push_back(t.st.nsec[d]);
+			for (i64 s = 0; s < t.st.nsec[d]; ++s)
+			{
+				v->st.sec_sizes.push_back(t.st.size_of(d, s));
+				const i64 *c = t.st.charge_of(d, s);
+				v->st.cvals.insert(v->st.cvals.end(), c, c + nc);
+			}
+		}
+		else
+		{
+			v->st.nsec.push_back((i64)sizes.size());
+			for (size_t k = 0; k < sizes.size(); ++k)
+			{
+				v->st.sec_sizes.push_back(sizes[k]);
+				const i64 *c = t.st.charge_of(d, out.parent[k]);
+				v->st.cvals.insert(v->st.cvals.end(), c, c + nc);
+			}
+		}
+	}
+	v->st.finalize();
+	// blocks: lexicographic order is preserved when the pieces of a block are emitted in place only if `dim` is the last
+	// differing position; in general re-sort
+	std::vector<i64> index, dims, strides, offs;
+	for (i64 b = 0; b < t.nblocks; ++b)
+	{
+		const i64 s = t.idx(b)[dim];
+		for (i64 k = first_sub[s]; k < first_sub[s + 1]; ++k)
+		{
+			for (i64 d = 0; d < r; ++d)
+			{
+				index.push_back(d == dim ? k : t.idx(b)[d]);
+				dims.push_back(d == dim ? sizes[k] : t.dm(b)[d]);
+				strides.push_back(t.sd(b)[d]);
+			}
+			offs.push_back(t.offs[b] + out.start[k] * t.sd(b)[dim]);
+		}
+	}
+	const i64 nb = (i64)offs.size();
+	std::vector<i64> sorted_index = index;
+	const auto order = r > 0 ? sort_blocks(r, sorted_index) : std::vector<i64>(nb, 0);
+	v->nblocks = nb;
+	v->index = sorted_index;
+	v->dims.resize(nb * r);
+	v->strides.resize(nb * r);
+	v->offs.resize(nb);
+	for (i64 k = 0; k < nb; ++k)
+	{
+		const i64 o = order[k];
+		std::copy(dims.begin() + o * r, dims.begin() + (o + 1) * r, v->dims.begin() + k * r);
+		std::copy(strides.begin() + o * r, strides.begin() + (o + 1) * r, v->strides.begin() + k * r);
+		v->offs[k] = offs[o];
+	}
+	v->arena = t.arena;
+	v->compute_hash();
+	out.t = std::move(v);
+	return out;
+}
+
+constexpr i64 kShardPiece = 128; // rows of a piece of the carried leg: the row extent of the large GEMM tile
+
 std::unique_ptr<Tensor> run_chain(Ctx &ctx, const Tensor &first, const Tensor *const rhs[3], const ChainStep steps[3])
 {
 	if (ctx.world <= 1)
@@ -209,21 +314,119 @@ std::unique_ptr<Tensor> run_chain(Ctx &ctx, const Tensor &first, const Tensor *c
 		auto t2 = tensordot(ctx, *t1, *rhs[1], steps[1].da, steps[1].db);
 		return tensordot(ctx, *t2, *rhs[2], steps[2].da, steps[2].db);
 	}
+	// where does the carried leg enter? output dims of a contraction = free dims of A (ascending), then free dims of B
+	const i64 ra = first.st.rank;
+	std::vector<char> ca(ra, 0), cb(rhs[0]->st.rank, 0);
+	for (auto d : steps[0].da)
+		ca[d < 0 ? d + ra : d] = 1;
+	for (auto d : steps[0].db)
+		cb[d < 0 ? d + rhs[0]->st.rank : d] = 1;
+	std::vector<std::pair<int, i64>> outdims; // (operand, dim)
+	for (i64 d = 0; d < ra; ++d)
+		if (!ca[d])
+			outdims.push_back({0, d});
+	for (i64 d = 0; d < rhs[0]->st.rank; ++d)
+		if (!cb[d])
+			outdims.push_back({1, d});
+	const auto src = outdims[steps[0].owner_dim];
+	static const bool msplit = !(std::getenv("QTB_SHARD_MSPLIT") && std::atoi(std::getenv("QTB_SHARD_MSPLIT")) == 0);
+	const bool refine = msplit && steps[2].owner_dim == 0;
+	Refined ref;
+	const Tensor *A0 = &first, *B0 = rhs[0];
+	if (refine)
+	{
+		ref = refine_leg(src.first == 0 ? first : *rhs[0], src.second, kShardPiece);
+		(src.first == 0 ? A0 : B0) = ref.t.get();
+	}
 	std::shared_ptr<Plan> plans[3];
-	plans[0] = get_plan(ctx, first, *rhs[0], steps[0].da, steps[0].db);
+	plans[0] = get_plan(ctx, *A0, *B0, steps[0].da, steps[0].db);
 	plans[1] = get_plan(ctx, plans[0]->out_proto, *rhs[1], steps[1].da, steps[1].db);
 	plans[2] = get_plan(ctx, plans[1]->out_proto, *rhs[2], steps[2].da, steps[2].db);
 	std::vector<double> w;
 	for (int i = 0; i < 3; ++i)
 		add_section_weights(*plans[i], steps[i].owner_dim, w);
 	const auto owner = lpt_assign(w, ctx.world);
-	auto t1 = tensordot_owned(ctx, plans[0], first, *rhs[0], steps[0].owner_dim, owner);
-	auto t2 = tensordot_owned(ctx, plans[1], *t1, *rhs[1], steps[1].owner_dim, owner);
+	// the carried leg keeps its sector through the chain: a rank only ever reads the intermediate blocks it wrote itself
+	auto t1 = tensordot_owned(ctx, plans[0], *A0, *B0, steps[0].owner_dim, owner, false);
+	auto t2 = tensordot_owned(ctx, plans[1], *t1, *rhs[1], steps[1].owner_dim, owner, false);
 	t1.reset();
-	auto t3 = tensordot_owned(ctx, plans[2], *t2, *rhs[2], steps[2].owner_dim, owner);
+	if (!refine)
+	{
+		auto t3 = tensordot_owned(ctx, plans[2], *t2, *rhs[2], steps[2].owner_dim, owner);
+		t2.reset();
+		ctx.allreduce(t3->arena->ptr, t3->arena->numel);
+		return t3;
+	}
+	// The result keeps the UNREFINED structure (bit-exact with the reference): every refined output block is a contiguous
+	// row slab of the block it refines (the carried leg is the slowest dim of the result), so the last step writes its
+	// tiles straight into the unrefined packed layout.
+	std::shared_ptr<Plan> up[3];
+	up[0] = get_plan(ctx, first, *rhs[0], steps[0].da, steps[0].db);
+	up[1] = get_plan(ctx, up[0]->out_proto, *rhs[1], steps[1].da, steps[1].db);
+	up[2] = get_plan(ctx, up[1]->out_proto, *rhs[2], steps[2].da, steps[2].db);
+	const Tensor &fin = up[2]->out_proto, &rfin = plans[2]->out_proto;
+	std::vector<i64> c_off(rfin.nblocks), fin_off(rfin.nblocks);
+	std::vector<i64> uidx(fin.st.rank);
+	for (i64 b = 0; b < rfin.nblocks; ++b)
+	{
+		const i64 k = rfin.idx(b)[0];
+		std::copy(rfin.idx(b), rfin.idx(b) + rfin.st.rank, uidx.begin());
+		uidx[0] = ref.parent[k];
+		const i64 ub = fin.find_block(uidx.data());
+		QTB_REQUIRE(ub >= 0, QTB_ERR_RUNTIME, "sharded chain: a refined output block has no parent block");
+		const i64 row = fin.block_numel(ub) / std::max<i64>(fin.dm(ub)[0], 1);
+		fin_off[b] = fin.offs[ub] + ref.start[k] * row;
+	}
+	auto out = std::make_unique<Tensor>(fin);
+	out->arena = std::make_shared<Arena>(&ctx, up[2]->out_numel);
+	bool any_empty = false;
+	for (auto &o : plans[2]->outs)
+		any_empty |= (o.pair_begin == o.pair_end);
+	const bool gather = ctx.nccl_comm != nullptr && !any_empty &&
+	                    !(std::getenv("QTB_SHARD_ALLREDUCE") && std::atoi(std::getenv("QTB_SHARD_ALLREDUCE")) == 1);
+	if (gather)
+	{ // Every rank writes its row slabs back to back into its chunk of a staging buffer (the last GEMM's output offsets are
+	  // remapped), ONE in-place ncclAllGather makes the staging buffer whole on every rank — exactly the owned bytes cross
+	  // NVLink — and a copy kernel puts the slabs at their place in the result's packed layout.
+		std::vector<i64> fill(ctx.world, 0), local(rfin.nblocks);
+		for (i64 b = 0; b < rfin.nblocks; ++b)
+		{
+			const int o = owner[rfin.idx(b)[0]];
+			local[b] = fill[o];
+			fill[o] += rfin.block_numel(b);
+		}
+		const i64 chunk = (*std::max_element(fill.begin(), fill.end()) + 1) & ~i64(1);
+		double *stage = (double *)ctx_alloc(ctx, (size_t)std::max<i64>(chunk * ctx.world, 1) * sizeof(double));
+		std::vector<GatherDesc> gd;
+		for (i64 b = 0; b < rfin.nblocks; ++b)
+		{
+			const int o = owner[rfin.idx(b)[0]];
+			c_off[b] = (i64)o * chunk + local[b];
+			GatherDesc g{};
+			g.src_off = c_off[b];
+			g.dst_off = fin_off[b];
+			g.numel = rfin.block_numel(b);
+			g.rank = 1;
+			g.dims[0] = g.numel;
+			g.strides[0] = 1;
+			if (g.numel > 0)
+				gd.push_back(g);
+		}
+		tensordot_owned_into(ctx, plans[2], *t2, *rhs[2], steps[2].owner_dim, owner, c_off, stage);
+		t2.reset();
+		if (chunk > 0)
+			nccl_allgather(ctx, stage, chunk);
+		launch_gather(ctx, gd, stage, out->arena->ptr);
+		ctx_free(ctx, stage);
+		ctx.counters[0] += 1;
+		return out;
+	}
+	if (up[2]->out_numel)
+		QTB_CUDA(cudaMemsetAsync(out->arena->ptr, 0, up[2]->out_numel * sizeof(double), ctx.stream));
+	tensordot_owned_into(ctx, plans[2], *t2, *rhs[2], steps[2].owner_dim, owner, fin_off, out->arena->ptr);
 	t2.reset();
-	ctx.allreduce(t3->arena->ptr, t3->arena->numel);
-	return t3;
+	ctx.allreduce(out->arena->ptr, out->arena->numel);
+	return out;
 }
 } // namespace
 

@@ -75,6 +75,8 @@ _SIGS = [
     ("qtb_ctx_stream", vp, [vp]),
     ("qtb_ctx_counters", C.c_int, [vp, p_i64]),
     ("qtb_ctx_set_sharding", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("qtb_nccl_unique_id", C.c_int, [C.c_char_p, C.c_char_p]),
+    ("qtb_ctx_init_nccl", C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     ("qtb_lpt_assign", C.c_int, [i64, p_f64, C.c_int, C.POINTER(C.c_int32)]),
     ("qtb_tensor_create", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, p_f64, C.POINTER(vp)]),
     ("qtb_tensor_adopt", C.c_int, [vp, i64, i64, p_i64, p_i64, p_i64, p_i64, p_i64, i64, p_i64, C.POINTER(vp), p_i64,
@@ -125,6 +127,13 @@ EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def nccl_unique_id(libnccl_path: Optional[str] = None) -> bytes:
+    """ncclGetUniqueId through the engine's dlopen'ed libnccl (rank 0 calls it, the bytes are broadcast by the host)"""
+    buf = C.create_string_buffer(128)
+    _check(load_library().qtb_nccl_unique_id(libnccl_path.encode() if libnccl_path else None, buf))
+    return buf.raw
 
 
 def lpt_assign(weights: Sequence[float], world: int) -> List[int]:
@@ -226,6 +235,13 @@ class Context:
 
         self._ar_cb = ALLREDUCE_FN(_cb)  # keep the trampoline alive as long as the context uses it
         _check(self.lib.qtb_ctx_set_sharding(self.h, int(rank), int(world), C.cast(self._ar_cb, C.c_void_p), None))
+        self.rank, self.world = int(rank), int(world)
+
+    def init_nccl(self, rank: int, world: int, unique_id: bytes, libnccl_path: Optional[str] = None) -> None:
+        """collective: creates the engine's own NCCL communicator from the 128-byte id of nccl_unique_id()"""
+        assert len(unique_id) == 128
+        _check(self.lib.qtb_ctx_init_nccl(self.h, int(rank), int(world), unique_id,
+                                          libnccl_path.encode() if libnccl_path else None))
         self.rank, self.world = int(rank), int(world)
 
     def close(self) -> None:

@@ -18,7 +18,7 @@ class _DeviceBuffer:
                                          "strides": None}
 
 
-def enable_sharding(ctx: Optional[Context] = None, group=None) -> Context:
+def enable_sharding(ctx: Optional[Context] = None, group=None, use_engine_nccl: bool = True) -> Context:
     """shard the engine's contractions and SVDs of `ctx` over the ranks of the torch.distributed process group `group`
     (default: the world group, backend nccl). Call after dist.init_process_group; one context per process."""
     import torch
@@ -39,6 +39,29 @@ def enable_sharding(ctx: Optional[Context] = None, group=None) -> Context:
         with torch.cuda.stream(ext):  # the collective is ordered after the engine's kernels and before its next ones
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
+    # fallback collective (a host callback into torch.distributed) first, then the engine's own NCCL communicator: with
+    # it no Python runs on the data path and the sharded contraction chains exchange exactly the owned row ranges
     ctx.set_sharding(rank, world, allreduce)
     ctx._sharding_keepalive = (ext, group)
+    if use_engine_nccl and dist.get_backend(group) == "nccl":
+        from .engine import nccl_unique_id
+
+        path = _find_libnccl()
+        box = [nccl_unique_id(path) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ctx.init_nccl(rank, world, box[0], path)
+        ctx.engine_nccl = True
     return ctx
+
+
+def _find_libnccl() -> Optional[str]:
+    """the libnccl.so.2 torch itself uses (pip wheels ship it under nvidia/nccl/lib); None = let dlopen search"""
+    import glob
+    import os
+    import sys
+
+    for base in sys.path:
+        hits = glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2"))
+        if hits:
+            return hits[0]
+    return None
