@@ -179,6 +179,8 @@ def run_reference(args, rank, world):
             "steps": len(ms), "warmup": args.warmup, "ms_per_step": t, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, **cfg, "flops_per_step": flops},
+            "details": {"note": "the reference is a single-host CPU implementation: with --gpus N the host runs the same "
+                                "contraction back to back, its rate (value) does not depend on N"},
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind,
                              "sample": f"{len(ms)} full {args.workload} contractions (whole workload, no sub-sampling)"},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -369,6 +371,43 @@ def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20, with_reference
     return out
 
 
+def time_svd_sweep(torch, qb, ctx, Ds, ref_max_D=1024):
+    """T4 of SURVEY.md section 8d: svd(theta, 2, tol = 1e-10, min = 4, max = D) of a Hubbard-profile two-site tensor
+    (U(1) x U(1), ~30-45 sectors per bond), D = 512 ... 8192; the compiled reference's svd on the host CPU beside it up to
+    ref_max_D. Wall time of the synchronous call (second of two calls)."""
+    from quantit_b200 import workloads as wl
+    out = {}
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    for D in Ds:
+        th = wl.hubbard_theta(D, np.random.default_rng(7))
+        T = qb.BTensor.from_host(**th, ctx=ctx)
+        ts = []
+        for _ in range(2):
+            ctx.sync()
+            t0 = time.perf_counter()
+            U, d, V = qb.svd(T, 2, 1e-10, 4, D)
+            ctx.sync()
+            ts.append(time.perf_counter() - t0)
+        rec = {"ms": ts[-1] * 1e3, "kept": int(sum(d.structure()[0][0])), "blocks": T.nblocks,
+               "bond_sectors": len(th["sec_sizes"][0]), "stored_MB": wl.stored_bytes(th) / 1e6}
+        if D <= ref_max_D and os.path.exists(harness):
+            with tempfile.TemporaryDirectory() as td:
+                pth = os.path.join(td, "theta.qtbt")
+                dump_qtbt(th, pth)
+                threads = os.cpu_count() or 1
+                r = subprocess.run([harness, "svdt", pth, "2", "1e-10", "4", str(D), "2.0", os.path.join(td, "U"),
+                                    os.path.join(td, "d"), os.path.join(td, "V"), "--reps", "1", "--threads", str(threads)],
+                                   capture_output=True, text=True, timeout=900)
+                tm = [float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("TIME_MS")]
+                if r.returncode == 0 and tm:
+                    rec["cpu_reference_ms"] = tm[-1]
+                    rec["cpu_threads"] = threads
+        out[f"D{D}"] = rec
+        del T, U, d, V
+        ctx.trim_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,11 +467,23 @@ def main():
 
     sharded = None
     if dist is not None and not args.no_extra:
-        # strong scaling of ONE H_eff.psi at D=4096 over the ranks (charge-sector sharding + one NCCL allreduce)
+        # strong scaling of ONE H_eff.psi at D=4096 over the ranks: row ranges of the bra bond owned per rank through the
+        # three contractions, the engine's own NCCL all-gather of the owned row slabs (quantit_b200/sharding.py). The
+        # same call unsharded on one GPU is timed in the same run for the efficiency.
         from quantit_b200.sharding import enable_sharding
+        single = time_heff(torch, qb, ctx, 15, 4096, 1.6, 5, 3, flush_buf, dist)
         enable_sharding(ctx)
         sharded = time_heff(torch, qb, ctx, 15, 4096, 1.6, 5, 3, flush_buf, dist)
         ctx.set_sharding(0, 1, None)
+        flops1 = single["flops_per_step"] / world  # every rank ran the whole contraction in the unsharded pass
+        sharded["flops_per_step"] = int(flops1)
+        sharded["value"] = flops1 / (sharded["ms_per_step"] * 1e-3) / 1e12
+        sharded["single_gpu_ms_per_step"] = single["ms_per_step"]
+        sharded["speedup"] = single["ms_per_step"] / sharded["ms_per_step"]
+        sharded["efficiency"] = sharded["speedup"] / world
+        sharded["scaling"] = "strong"
+        sharded["exchange"] = "ncclAllGather of the owned row slabs issued by the engine (dlopen'ed libnccl)" if getattr(
+            ctx, "engine_nccl", False) else "allreduce callback (torch.distributed)"
 
     e2e_ms, h2d, d2h = time_e2e(torch, qb, ctx, w, max(3, min(args.steps, 10)), 2)
     if dist is not None:
@@ -444,10 +495,12 @@ def main():
     line = {"metric": "block_tensordot_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, **w["cfg"],
-                       "flops_per_step": flops, "block_gemms": w["info"]["pairs"], "out_blocks": w["info"]["out_blocks"],
-                       "l2": "flushed between steps (256 MiB write outside the per-step CUDA-event pair)",
-                       "parallelism": f"{world} independent contraction(s), one per GPU"},
+            "config": {"workload": WORKLOAD_DESC[args.workload], "name": args.workload, **w["cfg"], "flops_per_step": flops},
+            "details": {"block_gemms": w["info"]["pairs"], "out_blocks": w["info"]["out_blocks"],
+                        "l2": "flushed between steps (256 MiB write outside the per-step CUDA-event pair)",
+                        "parallelism": f"{world} independent contraction(s), one per GPU (the headline workload partitions "
+                                       "into independent objects: no data-path collective; the sharded strong-scaling "
+                                       "measurement of ONE H_eff.psi is under strong_scaling)"},
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "qtb_tensordot_host (C ABI, pinned host buffers)"},
             "gpu_launches": w["launches"], "clocks": clocks}
@@ -473,9 +526,9 @@ def main():
             pass
         if sharded is not None:
             sharded["roofline_frac_aggregate"] = sharded["value"] / (world * peak)
-            sharded["workload"] = ("ONE H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO) sharded over %d GPUs by "
-                                   "charge sector of the bra bond, one allreduce of the result; strong scaling" % world)
-            line["workloads"] = {"heff_D4096_sharded": sharded}
+            sharded["workload"] = ("ONE H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO) sharded over %d GPUs: "
+                                   "row ranges of the bra bond owned per rank, one all-gather of the result" % world)
+            line["strong_scaling"] = sharded
         if not args.no_extra and world == 1:
             extra = {}
             for name in ["T2"] if args.workload != "T2" else ["T1"]:
@@ -488,6 +541,10 @@ def main():
             hf["roofline_frac"] = hf["value"] / peak
             hf["workload"] = "H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO): 3 block contractions"
             extra["heff_D4096"] = hf
+            try:
+                extra["svd_sweep_hubbard"] = time_svd_sweep(torch, qb, ctx, [512, 1024, 2048, 4096])
+            except Exception as e:  # noqa: BLE001
+                extra["svd_sweep_hubbard"] = {"error": repr(e)[:300]}
             for spec in [x for x in args.dmrg.split(";") if x.strip()]:
                 Ld, Dd, nsw = (int(x) for x in spec.split(","))
                 try:  # a side measurement must never cost the headline line

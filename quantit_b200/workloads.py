@@ -226,3 +226,33 @@ def random_mps(L: int, bond: int, target: int, seed: int = 0):
     for key in sites[0]["blocks"]:
         sites[0]["blocks"][key] = sites[0]["blocks"][key] / nrm
     return sites
+
+
+# ---- T4: Hubbard-profile two-site tensor, U(1) x U(1) (charge N, 2 Sz) ------------------------------
+HUBBARD_SITE = ([1, 1, 1, 1], [(0, 0), (1, 1), (1, -1), (2, 0)])  # python_binding/exemples/dmrg.py:41
+
+
+def bond2d(D: int, n_filling: int, sigma_n: float = 1.6, sigma_s: float = 2.2, min_weight: float = 1e-2):
+    """bond leg with a 2-D Gaussian profile over (N, 2 Sz): sectors (n, s) with n + s even around (n_filling, 0), sizes
+    proportional to exp(-(n - n0)^2 / 2 sigma_n^2 - s^2 / 2 sigma_s^2), total D (the remainder goes to the centre)."""
+    secs = []
+    for n in range(n_filling - 8, n_filling + 9):
+        for s in range(-8, 9):
+            if (n + s) % 2:
+                continue
+            w = float(np.exp(-((n - n_filling) ** 2) / (2 * sigma_n ** 2) - (s ** 2) / (2 * sigma_s ** 2)))
+            if w >= min_weight:
+                secs.append(((n, s), w))
+    tot = sum(w for _, w in secs)
+    sizes = [max(1, int(round(D * w / tot))) for _, w in secs]
+    centre = max(range(len(secs)), key=lambda i: secs[i][1])
+    sizes[centre] += D - sum(sizes)
+    return (sizes, [q for q, _ in secs])
+
+
+def hubbard_theta(D: int, rng: np.random.Generator, n_filling: int = 10):
+    """theta = rand_like(shape(beta, site, site, beta'*)) with the Hubbard physical leg, selection rule (0, 0)"""
+    beta = bond2d(D, n_filling)
+    right = bond2d(D, n_filling + 2)  # the two sites add between 0 and 4 particles: centre the right bond on +2
+    return rand_like(shape([beta, HUBBARD_SITE, HUBBARD_SITE, conj_leg(right)], (0, 0)), rng)
+
