@@ -1204,6 +1204,15 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 				plan->tile_cost.push_back(c);
 			}
 	}
+	// Bulk (UBLKCP) staging pays with 128 x 128 tiles (runs of 1 KB); with 64 x 64 tiles the runs are 128-512 bytes and the
+	// per-request cost of the TMA unit makes it slower than LDGSTS (configs[1]: 81 us against 75 us, profiles/r2/s17.txt)
+	if (plan->tile_cfg != 1)
+	{
+		for (auto &pr : plan->pairs)
+			pr.shf = 0;
+		for (auto &t : plan->tiles)
+			t.shf0 = 0;
+	}
 	plan->ncta = std::max(1, std::min<int>((int)plan->tiles.size(), gemm_grid_limit(ctx, plan->tile_cfg)));
 	if (plan->tile_cfg == 2) // the skinny kernel walks the list grid-stride: items are uniform, no static schedule needed
 		plan->cta_begin.assign(1, 0);
