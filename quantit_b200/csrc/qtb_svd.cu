@@ -694,7 +694,8 @@ __device__ __forceinline__ void jacobi_cs_fast(double gxx, double gyy, double gx
 constexpr int kFB = 16;                 // column-block width of the fused path
 constexpr int kFP = 2 * kFB;            // panel width
 constexpr int kFClusterMax = 8;         // CTAs per pair: 1, 2, 4 or 8, chosen per call so that a step is one wave
-constexpr int kFThreads = 256;
+constexpr int kFWork = 256;               // worker threads of the fused kernel
+constexpr int kFThreads = kFWork + 32;  // + one warp that computes rotations one tournament round ahead
 constexpr int kFSub = 64;               // panel rows staged at a time
 constexpr int kFLd = kFSub + 4;         // == 4 mod 16
 constexpr int kFLdJ = kFP + 4;          // == 4 mod 16
@@ -705,12 +706,15 @@ __global__ void __launch_bounds__(kFThreads, 4)
                      double *__restrict__ gpart, double *__restrict__ rot, int *__restrict__ flags,
                      unsigned long long *offmax, double skip_tol, int inner_max, double inner_tol, long long *dbg)
 {
+	// kFWork = 256 worker threads (8 warps: the DMMA phases and the rotation sweeps) + one extra warp that computes the
+	// NEXT tournament round's rotations while the workers apply the current one (see phase 2)
 	__shared__ double sP[kFP * kFLd];
-	__shared__ double sG[kFP * kFLdG];
+	__shared__ double sGG[2 * kFP * kFLdG]; // the pair's Gram matrix, double buffered across rounds; later the rotation J (ld kFLdJ)
 	__shared__ double sJ[kFP * kFLdG];
-	__shared__ double sJ2[kFP * kFLdJ];
-	__shared__ double s_c[kFP / 2], s_s[kFP / 2], s_red[kFThreads / 32];
+	__shared__ double s_c[2][kFP / 2], s_s[2][kFP / 2], s_red[kFThreads / 32];
 	__shared__ int s_rank[kFP];
+	static_assert(2 * kFP * kFLdG >= kFP * kFLdJ, "the update's copy of J reuses the Gram buffers");
+	double *sJ2 = sGG;
 	cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
 	const int rank = (int)cluster.block_rank();
 	const int kFCluster = (int)cluster.num_blocks(); // launch attribute (cudaLaunchAttributeClusterDimension)
@@ -719,6 +723,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
 	const SvdGroup G = groups[it.group];
 	const int wi = block_width(G, it.bi), wj = block_width(G, it.bj), p = wi + wj;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+	const bool worker = tid < kFWork;
 	double *Xg = X + G.x_off;
 	auto gcol = [&](int c) { return c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi); };
 	const int nrows = G.m + G.n;
@@ -727,33 +732,37 @@ __global__ void __launch_bounds__(kFThreads, 4)
 	const int S = (((nrows + kFCluster - 1) / kFCluster) + 7) & ~7, sbeg = min(nrows, rank * S), send = min(nrows, sbeg + S);
 	// staging: kFSub rows x kFP columns per pass, fetched into registers one pass ahead of the tensor-core work on the
 	// previous pass (the panel comes from L2 / HBM: the latency of a pass is otherwise exposed twice per pass)
-	constexpr int kPer = kFP * kFSub / kFThreads;
+	constexpr int kPer = kFP * kFSub / kFWork;
 	auto fetch = [&](int r0, int nr, double (&v)[kPer])
 	{
+		if (!worker)
+			return;
 #pragma unroll
 		for (int k = 0; k < kPer; ++k)
 		{
-			const int e = tid + k * kFThreads, c = e / kFSub, r = e % kFSub;
+			const int e = tid + k * kFWork, c = e / kFSub, r = e % kFSub;
 			v[k] = (c < p && r < nr) ? Xg[(i64)gcol(c) * G.ld + r0 + r] : 0.0;
 		}
 	};
 	auto stage = [&](const double (&v)[kPer])
 	{
+		if (!worker)
+			return;
 #pragma unroll
 		for (int k = 0; k < kPer; ++k)
 		{
-			const int e = tid + k * kFThreads;
+			const int e = tid + k * kFWork;
 			sP[(e / kFSub) * kFLd + (e % kFSub)] = v[k];
 		}
 	};
 
-	long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tqA = 0;
+	long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
 	int dbg_rounds = 0;
 	if (dbg)
 		tq0 = clock64();
 	// ---- 1. partial Gram matrix over this CTA's rows of the A part ----
 	{
-		const int ai = warp >> 1, aj0 = (warp & 1) * 2;
+		const int ai = (warp & 7) >> 1, aj0 = (warp & 1) * 2;
 		double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 		double v[kPer];
 		if (gbeg < gend)
@@ -764,23 +773,29 @@ __global__ void __launch_bounds__(kFThreads, 4)
 			__syncthreads();
 			if (r0 + kFSub < gend)
 				fetch(r0 + kFSub, min(kFSub, gend - r0 - kFSub), v);
-#pragma unroll 4
-			for (int kk = 0; kk < kFSub; kk += 4)
+			if (worker)
 			{
-				const double af = sP[(ai * 8 + g) * kFLd + kk + q];
-#pragma unroll
-				for (int j = 0; j < 2; ++j)
+#pragma unroll 4
+				for (int kk = 0; kk < kFSub; kk += 4)
 				{
-					const double bf = sP[((aj0 + j) * 8 + g) * kFLd + kk + q];
-					svd_dmma(acc[j][0], acc[j][1], af, bf);
+					const double af = sP[(ai * 8 + g) * kFLd + kk + q];
+#pragma unroll
+					for (int j = 0; j < 2; ++j)
+					{
+						const double bf = sP[((aj0 + j) * 8 + g) * kFLd + kk + q];
+						svd_dmma(acc[j][0], acc[j][1], af, bf);
+					}
 				}
 			}
 			__syncthreads();
 		}
-		double *gp = gpart + ((size_t)item_id * kFCluster + rank) * kFP * kFP;
+		if (worker)
+		{
+			double *gp = gpart + ((size_t)item_id * kFCluster + rank) * kFP * kFP;
 #pragma unroll
-		for (int j = 0; j < 2; ++j)
-			*reinterpret_cast<double2 *>(gp + (ai * 8 + g) * kFP + (aj0 + j) * 8 + 2 * q) = make_double2(acc[j][0], acc[j][1]);
+			for (int j = 0; j < 2; ++j)
+				*reinterpret_cast<double2 *>(gp + (ai * 8 + g) * kFP + (aj0 + j) * 8 + 2 * q) = make_double2(acc[j][0], acc[j][1]);
+		}
 	}
 	__threadfence();
 	cluster.sync();
@@ -790,6 +805,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
 	// ---- 2. CTA 0: gauge + eigen-decomposition of the pair's Gram matrix ----
 	if (rank == 0)
 	{
+		double *sG = sGG; // current buffer; the rounds ping-pong between sGG and sGG + kFP * kFLdG
 		const double *gp = gpart + (size_t)item_id * kFCluster * kFP * kFP;
 		for (int e = tid; e < kFP * kFP; e += kFThreads)
 		{
@@ -831,7 +847,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
 		if (work)
 		{
 			const int pe = (p + 1) & ~1, npair = pe / 2;
-			const int bw = tid >> 4, bq = tid & 15; // this thread's 2x2 block: (pair bw) x (pair bq)
+			const int bw = tid >> 4, bq = tid & 15; // a worker's 2x2 block: (pair bw) x (pair bq)
 			auto pair_of = [&](int step, int k, int &x, int &y)
 			{ // tournament: player pe-1 fixed, the others rotate
 				if (k == 0)
@@ -847,66 +863,127 @@ __global__ void __launch_bounds__(kFThreads, 4)
 					y = y < 0 ? y + (pe - 1) : y;
 				}
 			};
+			// which pair of round `step` holds player v, and on which side (0: the x member, 1: the y member)
+			auto where_is = [&](int step, int v, int &k, int &side)
+			{
+				if (v == pe - 1)
+				{
+					k = 0;
+					side = 0;
+					return;
+				}
+				if (v == step)
+				{
+					k = 0;
+					side = 1;
+					return;
+				}
+				int dk = v - step;
+				dk = dk < 0 ? dk + (pe - 1) : dk;
+				if (dk <= npair - 1)
+				{
+					k = dk;
+					side = 0;
+				}
+				else
+				{
+					k = pe - 1 - dk;
+					side = 1;
+				}
+			};
 			// What a sweep leaves of an element of relative size g is ~ g^2: another inner sweep only pays while the elements
 			// met are above inner_tol x the gauge this visit started from (and never below the rotation threshold)
 			const double again_thr = fmax(1e-30, fmin(1e-2, inner_tol * gauge));
+			auto rotation_from = [&](double gxx, double gyy, double gxy, double &cs, double &sn, int &big)
+			{
+				cs = 1.0;
+				sn = 0.0;
+				const double sc2 = fabs(gxx * gyy), g2 = gxy * gxy;
+				if (g2 > 1e-34 * sc2 && gxy != 0.0)
+				{
+					jacobi_cs_fast(gxx, gyy, gxy, cs, sn);
+					if (g2 >= again_thr * sc2)
+						big = 1; // this sweep meets an element large enough to warrant another one
+				}
+			};
+			int cur = 0;     // rotation / Gram buffers of the round being applied
+			int rotated = 0; // (extra warp) a rotation of the sweep in progress was "big"
+			// rotations of the very first round, straight from G
+			if (warp == 8 && lane < npair)
+			{
+				int x, y;
+				pair_of(0, lane, x, y);
+				double cs = 1.0, sn = 0.0;
+				if (x < p && y < p)
+					rotation_from(sG[x * kFLdG + x], sG[y * kFLdG + y], sG[x * kFLdG + y], cs, sn, rotated);
+				s_c[0][lane] = cs;
+				s_s[0][lane] = sn;
+			}
+			__syncthreads();
 			for (int sweep = 0; sweep < inner_max; ++sweep)
 			{
-				int rotated = 0;
 				for (int step = 0; step < pe - 1; ++step)
 				{
 					++dbg_rounds;
-					long long ta = 0;
-					if (dbg)
-						ta = clock64();
-					// A: the rotations of the round, pair ak on lane ak / 8 of warp ak % 8 (spread over the warps: lanes of one
-					// warp taking different branches of the angle computation would be serialised)
-					const int ak = lane < 2 ? warp + 8 * lane : kFP;
-					if (ak < npair)
+					const double *Gc = sGG + cur * kFP * kFLdG;
+					double *Gn = sGG + (cur ^ 1) * kFP * kFLdG;
+					if (warp == 8)
 					{
-						int x, y;
-						pair_of(step, ak, x, y);
-						double cs = 1.0, sn = 0.0;
-						if (x < p && y < p)
+						// ---- A': the rotations of the NEXT round, from the current G and the rotations being applied now.
+						// The three entries a rotation needs are bilinear forms of 2x2 blocks of the current G; computing them
+						// here takes the ~1000-cycle angle computation off the critical path of the round.
+						if (lane < npair)
 						{
-							const double gxy = sG[x * kFLdG + y], gxx = sG[x * kFLdG + x], gyy = sG[y * kFLdG + y];
-							const double sc2 = fabs(gxx * gyy), g2 = gxy * gxy;
-							if (g2 > 1e-34 * sc2 && gxy != 0.0)
+							const int nstep = step + 1 < pe - 1 ? step + 1 : 0;
+							int x, y;
+							pair_of(nstep, lane, x, y);
+							double cs = 1.0, sn = 0.0;
+							if (x < p && y < p)
 							{
-								jacobi_cs_fast(gxx, gyy, gxy, cs, sn);
-								if (g2 >= again_thr * sc2)
-									rotated = 1; // this sweep met an element large enough to warrant another one
+								int ka, sa, kb, sb;
+								where_is(step, x, ka, sa);
+								where_is(step, y, kb, sb);
+								if (ka != kb)
+								{
+									int xa, ya, xb, yb;
+									pair_of(step, ka, xa, ya);
+									pair_of(step, kb, xb, yb);
+									const double ca = s_c[cur][ka], sna = s_s[cur][ka], cb = s_c[cur][kb], snb = s_s[cur][kb];
+									// new row / column v = alpha_x * (x member) + alpha_y * (y member):  x' = c x - s y,  y' = s x + c y
+									const double ax = sa ? sna : ca, ay = sa ? ca : -sna;
+									const double bx = sb ? snb : cb, by = sb ? cb : -snb;
+									const double gaa_xx = Gc[xa * kFLdG + xa], gaa_xy = Gc[xa * kFLdG + ya], gaa_yy = Gc[ya * kFLdG + ya];
+									const double gbb_xx = Gc[xb * kFLdG + xb], gbb_xy = Gc[xb * kFLdG + yb], gbb_yy = Gc[yb * kFLdG + yb];
+									const double g00 = Gc[xa * kFLdG + xb], g01 = Gc[xa * kFLdG + yb];
+									const double g10 = Gc[ya * kFLdG + xb], g11 = Gc[ya * kFLdG + yb];
+									const double nxx = ax * (ax * gaa_xx + 2.0 * ay * gaa_xy) + ay * ay * gaa_yy;
+									const double nyy = bx * (bx * gbb_xx + 2.0 * by * gbb_xy) + by * by * gbb_yy;
+									const double nxy = ax * (bx * g00 + by * g01) + ay * (bx * g10 + by * g11);
+									rotation_from(nxx, nyy, nxy, cs, sn, rotated);
+								}
+								// ka == kb: the same two players meet again (a 2-player tournament): their element was just annihilated
 							}
+							s_c[cur ^ 1][lane] = cs;
+							s_s[cur ^ 1][lane] = sn;
 						}
-						s_c[ak] = cs;
-						s_s[ak] = sn;
 					}
-					if (dbg)
-						tq4 += clock64() - ta; // phase A (thread-local)
-					__syncthreads();
-					if (dbg)
-						tqA += clock64() - ta; // phase A as the CTA sees it (slowest warp + barrier)
-					if (bw < npair && bq < npair)
-					{ // B: G <- T^T G T on the 2x2 block, J <- J T on two rows
+					else if (bw < npair && bq < npair)
+					{ // ---- B: G <- T^T G T on the 2x2 block (into the other buffer), J <- J T on two rows ----
 						int xw, yw, xq, yq;
 						pair_of(step, bw, xw, yw);
 						pair_of(step, bq, xq, yq);
-						const double cw = s_c[bw], sw = s_s[bw], cq = s_c[bq], sq = s_s[bq];
-						// every load of the round first, every store last: the fp64 / shared-memory latencies of this part are
-						// long (the whole round is a latency chain), so the three independent 2x2 updates must overlap
-						double *g0 = sG + xw * kFLdG, *g1 = sG + yw * kFLdG;
+						const double cw = s_c[cur][bw], sw = s_s[cur][bw], cq = s_c[cur][bq], sq = s_s[cur][bq];
+						const double *g0 = Gc + xw * kFLdG, *g1 = Gc + yw * kFLdG;
 						double *j0 = sJ + (2 * bw) * kFLdG, *j1 = j0 + kFLdG;
 						const double g00 = g0[xq], g01 = g0[yq], g10 = g1[xq], g11 = g1[yq];
 						const double a0x = j0[xq], a0y = j0[yq], a1x = j1[xq], a1y = j1[yq];
 						const double h00 = cw * g00 - sw * g10, h01 = cw * g01 - sw * g11; // rows: T_w^T from the left
 						const double h10 = sw * g00 + cw * g10, h11 = sw * g01 + cw * g11;
-						if (sw != 0.0 || sq != 0.0)
-						{
-							g0[xq] = cq * h00 - sq * h01; // columns: T_q from the right
-							g0[yq] = sq * h00 + cq * h01;
-							g1[xq] = cq * h10 - sq * h11;
-							g1[yq] = sq * h10 + cq * h11;
-						}
+						double *n0 = Gn + xw * kFLdG, *n1 = Gn + yw * kFLdG;
+						n0[xq] = cq * h00 - sq * h01; // columns: T_q from the right
+						n0[yq] = sq * h00 + cq * h01;
+						n1[xq] = cq * h10 - sq * h11;
+						n1[yq] = sq * h10 + cq * h11;
 						if (sq != 0.0)
 						{
 							j0[xq] = cq * a0x - sq * a0y;
@@ -916,22 +993,27 @@ __global__ void __launch_bounds__(kFThreads, 4)
 						}
 					}
 					__syncthreads();
+					cur ^= 1;
 				}
-				if (!__syncthreads_or(rotated))
+				// `rotated` lives in the extra warp; the flags of a sweep include its rounds' look-ahead (the first round of
+				// the next sweep instead of its own first round: immaterial for a stopping heuristic)
+				const int go = __syncthreads_or(rotated);
+				rotated = 0;
+				if (!go)
 					break;
 			}
-			__syncthreads();
+			const double *Gf = sGG + cur * kFP * kFLdG;
 			if (tid < kFP)
 			{ // descending eigenvalue order (de Rijk's ordering in block form)
 				const int k = tid;
 				int rk = k;
 				if (k < p)
 				{
-					const double dk = sG[k * kFLdG + k];
+					const double dk = Gf[k * kFLdG + k];
 					rk = 0;
 					for (int j = 0; j < p; ++j)
 					{
-						const double dj = sG[j * kFLdG + j];
+						const double dj = Gf[j * kFLdG + j];
 						rk += (dj > dk || (dj == dk && j < k)) ? 1 : 0;
 					}
 				}
@@ -960,9 +1042,6 @@ __global__ void __launch_bounds__(kFThreads, 4)
 			dbg[item_id * 8 + 1] = tq2 - tq1;
 			dbg[item_id * 8 + 2] = tq3 - tq2;
 			dbg[item_id * 8 + 3] = dbg_rounds;
-			dbg[item_id * 8 + 5] = tq4;
-			dbg[item_id * 8 + 6] = tqA;
-			tq4 = 0;
 		}
 	}
 	// ---- 3. every CTA rotates its rows of the [A;V] panel ----
@@ -970,9 +1049,10 @@ __global__ void __launch_bounds__(kFThreads, 4)
 		return;
 	{
 		const double *Jm = rot + (size_t)item_id * kFP * kFP;
+		__syncthreads(); // (CTA 0) everybody is done with the Gram buffers that sJ2 reuses
 		for (int e = tid; e < kFP * kFP; e += kFThreads)
 			sJ2[(e / kFP) * kFLdJ + (e % kFP)] = __ldcg(Jm + e);
-		const int rw0 = warp * 8;
+		const int rw0 = (warp & 7) * 8;
 		double v[kPer];
 		if (sbeg < send)
 			fetch(sbeg, min(kFSub, send - sbeg), v);
@@ -984,6 +1064,8 @@ __global__ void __launch_bounds__(kFThreads, 4)
 			__syncthreads();
 			if (r0 + kFSub < send)
 				fetch(r0 + kFSub, min(kFSub, send - r0 - kFSub), v);
+			if (!worker)
+				continue;
 			double acc[4][2];
 #pragma unroll
 			for (int j = 0; j < 4; ++j)
@@ -1012,10 +1094,7 @@ __global__ void __launch_bounds__(kFThreads, 4)
 		}
 	}
 	if (dbg && rank == 0 && tid == 0)
-	{
-		tq4 = clock64();
-		dbg[item_id * 8 + 4] = tq4 - tq3;
-	}
+		dbg[item_id * 8 + 4] = clock64() - tq3;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1512,7 +1591,10 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	// QR preconditioning (qtb_svd_qr.cuh) on the tensor-core path: the Jacobi iteration then runs on [R^T ; I] (2n x n)
 	const bool use_panel_early = (size_t)((rows_max | 1)) * 2 * jb * sizeof(double) <= kPanelSmemMax;
 	static const bool qr_env = !(std::getenv("QTB_SVD_QR") && std::atoi(std::getenv("QTB_SVD_QR")) == 0);
-	bool use_qr = qr_env && !use_panel_early && ng > 0;
+	// also on the shared-memory panel path once a group has more than two column blocks: 16 -> ~9 outer sweeps on the
+	// mid-size groups of a DMRG run (profiles/r2/s21.txt: -24 % / -31 % SVD time at bond dimension 256 / 512)
+	static const bool qr_panel_env = !(std::getenv("QTB_SVD_QR_PANEL") && std::atoi(std::getenv("QTB_SVD_QR_PANEL")) == 0);
+	bool use_qr = qr_env && (!use_panel_early || (qr_panel_env && cols_max > 2 * kJB)) && ng > 0;
 	for (i64 g = 0; g < ng && use_qr; ++g)
 		if (std::max(groups[g].m, groups[g].n) > (i64)kQrCluster * kQrSlabMax)
 			use_qr = false; // a panel would not fit the cluster's shared memory
@@ -1687,8 +1769,23 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 							max_cols2 = std::max(max_cols2, q.n - (k + 1) * kQrB);
 						}
 					}
-					const int SP = qr_slab_rows(max_rows) | 1;
-					qr_panel_kernel<<<cnt * kQrCluster, kQrThreads, qr_panel_smem(SP), ctx.stream>>>(d_qr, X, k, SP);
+					const int qcs = max_rows <= kQrSlabMax ? 1 : kQrCluster;
+					const int SP = qr_slab_rows(max_rows, qcs) | 1;
+					{
+						cudaLaunchConfig_t cfg = {};
+						cfg.gridDim = dim3((unsigned)(cnt * qcs));
+						cfg.blockDim = dim3(kQrThreads);
+						cfg.dynamicSmemBytes = qr_panel_smem(SP);
+						cfg.stream = ctx.stream;
+						cudaLaunchAttribute at[1];
+						at[0].id = cudaLaunchAttributeClusterDimension;
+						at[0].val.clusterDim.x = (unsigned)qcs;
+						at[0].val.clusterDim.y = 1;
+						at[0].val.clusterDim.z = 1;
+						cfg.attrs = at;
+						cfg.numAttrs = 1;
+						QTB_CUDA(cudaLaunchKernelEx(&cfg, qr_panel_kernel, (const QrGroup *)d_qr, X, k, SP));
+					}
 					ctx.counters[0] += 1;
 					if (cnt2 > 0)
 					{
@@ -1775,7 +1872,11 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			std::vector<i64> all_groups(ng);
 			std::iota(all_groups.begin(), all_groups.end(), i64(0));
 			const bool use_fused = !use_panel && jb == kFB && fused_env;
-			const int nlanes = (use_panel || use_fused) ? 1 : (int)std::max<size_t>(1, std::min<size_t>(lanes_max, all_groups.size()));
+			// fused path: lanes let one lane's latency-bound eigensolver phase overlap the other lanes' memory-bound Gram /
+			// update phases (the kernels of different lanes are concurrent: every cluster of a step is resident)
+			static const int fused_lanes = std::getenv("QTB_SVD_FLANES") ? std::max(1, std::atoi(std::getenv("QTB_SVD_FLANES"))) : 1;
+			const int nlanes = use_panel ? 1
+			                   : (int)std::max<size_t>(1, std::min<size_t>(use_fused ? fused_lanes : lanes_max, all_groups.size()));
 			std::vector<Lane> lanes(nlanes);
 			{
 				std::vector<i64> order = all_groups;
@@ -1866,7 +1967,10 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			{
 				static const int fc_env = std::getenv("QTB_SVD_FCLUSTER") ? std::atoi(std::getenv("QTB_SVD_FCLUSTER")) : 0;
 				const int resident = ctx.sm_count * 4 - ctx.sm_count / 4; // cluster placement never reaches the full count
-				while (fused_cluster < kFClusterMax && lanes[0].max_items * fused_cluster * 2 <= resident)
+				int items_all = 0;
+				for (auto &L : lanes)
+					items_all += L.max_items;
+				while (fused_cluster < kFClusterMax && items_all * fused_cluster * 2 <= resident)
 					fused_cluster *= 2;
 				if (fc_env == 1 || fc_env == 2 || fc_env == 4 || fc_env == 8)
 					fused_cluster = fc_env;
@@ -1936,8 +2040,8 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 										a[k] += (double)h[i * 8 + k] / cnt;
 										mx[k] = std::max(mx[k], (double)h[i * 8 + k]);
 									}
-								std::fprintf(stderr, "[qtb svd] fused phases (cycles, CTA 0 of %d clusters) sweep %d: gram+barrier avg %.0f max %.0f | eig avg %.0f max %.0f | barrier %.0f max %.0f | rounds avg %.1f max %.0f | update avg %.0f max %.0f | phase A total avg %.0f, with barrier %.0f\n",
-								             cnt, sweep, a[0], mx[0], a[1], mx[1], a[2], mx[2], a[3], mx[3], a[4], mx[4], a[5], a[6]);
+								std::fprintf(stderr, "[qtb svd] fused phases (cycles, CTA 0 of %d clusters) sweep %d: gram+barrier avg %.0f max %.0f | eig avg %.0f max %.0f | barrier %.0f max %.0f | rounds avg %.1f max %.0f | update avg %.0f max %.0f \n",
+								             cnt, sweep, a[0], mx[0], a[1], mx[1], a[2], mx[2], a[3], mx[3], a[4], mx[4]);
 								ctx_free(ctx, d_dbg);
 							}
 							ctx.counters[0] += 1;

@@ -55,23 +55,26 @@ __device__ __forceinline__ void qr_dmma(double &c0, double &c1, double a, double
 
 // shared memory of the panel kernel (doubles): P[32][SP] | exch[2][9][32] | T[32][33] | part[32]
 __host__ __device__ inline size_t qr_panel_smem(int SP) { return (size_t)(32 * SP + 2 * 9 * 32 + 32 * 33 + 32) * sizeof(double); }
-__host__ __device__ inline int qr_slab_rows(int mrows)
+__host__ __device__ inline int qr_slab_rows(int mrows, int cluster)
 { // rows per CTA of the cluster; at least the panel width so that every pivot row lives in CTA 0
-	int s = ((mrows + kQrCluster - 1) / kQrCluster + 7) & ~7;
+	int s = ((mrows + cluster - 1) / cluster + 7) & ~7;
 	return s < kQrB ? kQrB : s;
 }
 
-__global__ void __cluster_dims__(kQrCluster, 1, 1) __launch_bounds__(kQrThreads)
+// cluster size (launch attribute): kQrCluster for tall panels, 1 when the whole panel fits one CTA's shared memory (the
+// per-column cluster barrier is then a CTA barrier: small groups factorise ~2x faster)
+__global__ void __launch_bounds__(kQrThreads)
     qr_panel_kernel(const QrGroup *__restrict__ groups, double *__restrict__ ws, int k, int SPmax)
 {
 	extern __shared__ double qsm[];
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = (int)cluster.block_rank();
-	const QrGroup G = groups[blockIdx.x / kQrCluster];
+	const int CS = (int)cluster.num_blocks();
+	const QrGroup G = groups[blockIdx.x / CS];
 	const int r0 = k * kQrB;
 	const int w = min(kQrB, G.n - r0);
 	const int mrows = G.m - r0;
-	const int S = qr_slab_rows(mrows);
+	const int S = qr_slab_rows(mrows, CS);
 	const int SP = SPmax; // uniform carve-up of the dynamic shared memory
 	double *P = qsm;
 	double *exch = P + 32 * SP;
@@ -117,16 +120,18 @@ __global__ void __cluster_dims__(kQrCluster, 1, 1) __launch_bounds__(kQrThreads)
 		__syncthreads();
 		{ // all-to-all: thread (dest, c) stores this CTA's partial (and, from CTA 0, the pivot row) into CTA `dest`
 			const int dest = tid >> 5, c = tid & 31;
-			double *remote = cluster.map_shared_rank(exch, dest);
-			remote[(par * 9 + rank) * 32 + c] = part[c];
-			if (rank == 0)
-				remote[(par * 9 + 8) * 32 + c] = P[c * SP + j];
+			if (dest < CS)
+			{
+				double *remote = cluster.map_shared_rank(exch, dest);
+				remote[(par * 9 + rank) * 32 + c] = part[c];
+				if (rank == 0)
+					remote[(par * 9 + 8) * 32 + c] = P[c * SP + j];
+			}
 		}
 		cluster.sync();
 		const double *E = exch + par * 9 * 32;
 		double dj = 0.0;
-#pragma unroll
-		for (int rk = 0; rk < kQrCluster; ++rk)
+		for (int rk = 0; rk < CS; ++rk)
 			dj += E[rk * 32 + j];
 		const double alpha = E[8 * 32 + j];
 		double tau = 0.0, inv = 0.0, beta = alpha;
@@ -146,8 +151,7 @@ __global__ void __cluster_dims__(kQrCluster, 1, 1) __launch_bounds__(kQrThreads)
 				if (c > j && c < w)
 				{
 					double dc = 0.0;
-#pragma unroll
-					for (int rk = 0; rk < kQrCluster; ++rk)
+					for (int rk = 0; rk < CS; ++rk)
 						dc += E[rk * 32 + c];
 					const double wc = E[8 * 32 + c] + dc * inv; // v^T p_c
 					const double f = tau * wc * inv;
@@ -165,8 +169,7 @@ __global__ void __cluster_dims__(kQrCluster, 1, 1) __launch_bounds__(kQrThreads)
 			if (lane < j)
 			{
 				double dc = 0.0;
-#pragma unroll
-				for (int rk = 0; rk < kQrCluster; ++rk)
+				for (int rk = 0; rk < CS; ++rk)
 					dc += E[rk * 32 + lane];
 				s = E[8 * 32 + lane] + dc * inv; // v_lane^T v_j
 			}
