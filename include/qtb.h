@@ -233,6 +233,16 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
                     const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, double *sweep_energy,
                     double *sweep_seconds, int64_t *sweep_mid_bond);
 
+/* The same with a per-sweep callback in the role of the reference's dmrg_logger (include/dmrg_logger.h:22-60:
+ * it_log_all(iteration, E, state) after every sweep): `log(user, iteration, energy, seconds, bond_dims, n)` receives
+ * the n = length + 1 bond dimensions of the chain (left edge ... right edge). The adaptor forwards it to the caller's
+ * dmrg_logger object while the run is in progress. */
+typedef void (*qtb_dmrg_log_fn)(void *user, int64_t iteration, double energy, double seconds, const int64_t *bond_dims,
+                                int64_t n);
+qtb_status qtb_dmrg_logged(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_tensor **mps, int64_t *oc,
+                           const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, qtb_dmrg_log_fn log,
+                           void *user);
+
 /* <a|obs|b> (obs != NULL: `obs` holds `length` rank-4 MPO tensors) or <a|b> (obs == NULL) of two bMPS of `length` sites.
  * Replaces quantit::contract(const bMPS&, const bMPS&, const bMPO&) and contract(const bMPS&, const bMPS&)
  * (reference include/MPT.h:724-727, sources/MPT.cpp:211-233, 275-292: identity edges on the outer bonds, all-ones on

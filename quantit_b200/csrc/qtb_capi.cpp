@@ -577,6 +577,36 @@ qtb_status qtb_dmrg(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_te
 	    });
 }
 
+qtb_status qtb_dmrg_logged(qtb_ctx *ctx, int64_t length, qtb_tensor *const *mpo, qtb_tensor **mps, int64_t *oc,
+                           const qtb_dmrg_options *options, double *energy, int64_t *n_sweeps, qtb_dmrg_log_fn log,
+                           void *user)
+{
+	return guarded(ctx,
+	    [&]()
+	    {
+		    QTB_REQUIRE(ctx && mpo && mps && oc && options && energy && n_sweeps, QTB_ERR_INVALID_ARGUMENT, "null argument");
+		    std::vector<const Tensor *> H(length);
+		    std::vector<std::unique_ptr<Tensor>> psi(length);
+		    for (int64_t i = 0; i < length; ++i)
+		    {
+			    H[i] = mpo[i]->t.get();
+			    psi[i] = std::move(mps[i]->t);
+		    }
+		    try
+		    {
+			    dmrg(ctx->c, length, H.data(), psi, *oc, *options, *energy, *n_sweeps, nullptr, nullptr, nullptr, log, user);
+		    }
+		    catch (...)
+		    {
+			    for (int64_t i = 0; i < length; ++i)
+				    mps[i]->t = std::move(psi[i]);
+			    throw;
+		    }
+		    for (int64_t i = 0; i < length; ++i)
+			    mps[i]->t = std::move(psi[i]);
+	    });
+}
+
 qtb_status qtb_contract(qtb_ctx *ctx, int64_t length, qtb_tensor *const *a, qtb_tensor *const *b, qtb_tensor *const *obs,
                         double *result)
 {

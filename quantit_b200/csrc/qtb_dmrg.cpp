@@ -200,7 +200,7 @@ void coalesce(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mpo, double cutoff
 
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
-          i64 *sweep_mid_bond)
+          i64 *sweep_mid_bond, qtb_dmrg_log_fn log_fn, void *log_user)
 {
 	QTB_REQUIRE(L >= 2, QTB_ERR_INVALID_ARGUMENT, "dmrg: at least two sites are required");
 	for (i64 i = 0; i < L; ++i)
@@ -232,11 +232,11 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 	int step = (oc == 0) ? 1 : -1;
 	if (nh == 1)
 		step = 0;
-	const i64 init_pos = oc;
-	QTB_REQUIRE(oc != L - 1 || L == 2, QTB_ERR_RUNTIME,
-	            "dmrg: an orthogonality centre on the last site needs bMPS::move_oc afterwards (not on this path)");
+	// a centre on the last site: the reference steps it back by one without regauging (dmrg.cpp:229-233) — the two-site
+	// tensor of sites (L-2, L-1) is the centre either way, the left environments up to L-3 and the right edge are in place
 	if (oc == L - 1)
 		--oc;
+	const i64 init_pos = oc;
 	double *d_scal = (double *)ctx_alloc(ctx, 2 * sizeof(double));
 	n_sweeps = 0;
 	// QTB_PROFILE=1: per-phase wall time with a stream sync after every phase (diagnostics only, perturbs the timing)
@@ -313,14 +313,21 @@ void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr
 		if (sweep_mid_bond)
 			sweep_mid_bond[it] = mps[L / 2]->st.dim_size(0);
 		n_sweeps = it + 1;
+		if (log_fn) // dmrg_logger::it_log_all (dmrg.cpp:243): energy, bond dimensions, wall time of the sweep
+		{
+			std::vector<i64> bonds(L + 1);
+			for (i64 i = 0; i < L; ++i)
+				bonds[i] = mps[i]->st.dim_size(0);
+			bonds[L] = mps[L - 1]->st.dim_size(2);
+			log_fn(log_user, it, E, secs, bonds.data(), L + 1);
+		}
 		const double Eold = E0;
 		E0 = E;
 		if (!(std::fabs((E0 - Eold) / E0) > opt.convergence_criterion)) // stops on NaN too (dmrg.cpp:247-254)
 			break;
 	}
 	ctx_free(ctx, d_scal);
-	QTB_REQUIRE(oc == init_pos || (init_pos == L - 1), QTB_ERR_RUNTIME,
-	            "the orthogonality center finished somewhere surprising!");
+	QTB_REQUIRE(oc == init_pos, QTB_ERR_RUNTIME, "the orthogonality center finished somewhere surprising!");
 	energy = E0;
 }
 

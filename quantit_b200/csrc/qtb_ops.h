@@ -47,5 +47,5 @@ void move_oc(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc, i64 t
 void coalesce(Ctx &ctx, std::vector<std::unique_ptr<Tensor>> &mpo, double cutoff);
 void dmrg(Ctx &ctx, i64 L, const Tensor *const *mpo, std::vector<std::unique_ptr<Tensor>> &mps, i64 &oc,
           const qtb_dmrg_options &opt, double &energy, i64 &n_sweeps, double *sweep_energy, double *sweep_seconds,
-          i64 *sweep_mid_bond);
+          i64 *sweep_mid_bond, qtb_dmrg_log_fn log_fn = nullptr, void *log_user = nullptr);
 } // namespace qtb

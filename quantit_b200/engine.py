@@ -119,6 +119,7 @@ _SIGS = [
     ("qtb_env_right", C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     ("qtb_two_sites_update", C.c_int, [vp, vp, vp, vp, vp, p_f64, C.POINTER(vp)]),
     ("qtb_dmrg", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, p_f64, p_f64, p_i64]),
+    ("qtb_dmrg_logged", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), p_i64, vp, p_f64, p_i64, C.c_void_p, C.c_void_p]),
     ("qtb_contract", C.c_int, [vp, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), p_f64]),
     ("qtb_move_oc", C.c_int, [vp, i64, C.POINTER(vp), p_i64, i64]),
     ("qtb_coalesce", C.c_int, [vp, i64, C.POINTER(vp), C.c_double]),
@@ -601,6 +602,34 @@ def dmrg(hamiltonian: List[BTensor], in_out_state: List[BTensor], options: dmrg_
         log["mid_bond"] = [sb[i] for i in range(ns.value)]
         log["oc"] = occ.value
     return E.value
+
+
+DMRG_LOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_int64), C.c_int64)
+
+
+def dmrg_logged(hamiltonian: List[BTensor], in_out_state: List[BTensor], options: dmrg_options, logger, oc: int = 0):
+    """quantit::dmrg with a dmrg_logger (reference include/dmrg_logger.h): `logger(iteration, energy, seconds, bond_dims)`
+    is called after every sweep while the run is in progress. Returns (energy, sweeps, final centre)."""
+    ctx = in_out_state[0].ctx
+    L = len(hamiltonian)
+    H = (vp * L)(*[t.h for t in hamiltonian])
+    P = (vp * L)(*[t.h for t in in_out_state])
+    o = DmrgOptionsC(options.cutoff, options.convergence_criterion,
+                     -1 if options.maximum_bond is None else int(options.maximum_bond), int(options.minimum_bond),
+                     int(options.maximum_iterations))
+
+    def _cb(user, it, e, secs, bonds, n):
+        try:
+            logger(int(it), float(e), float(secs), [int(bonds[i]) for i in range(n)])
+        except Exception:  # no exception may cross the C ABI
+            import traceback
+            traceback.print_exc()
+
+    cb = DMRG_LOG_FN(_cb)
+    e, ns, occ = C.c_double(), i64(), i64(oc)
+    _check(ctx.lib.qtb_dmrg_logged(ctx.h, L, H, P, C.byref(occ), C.byref(o), C.byref(e), C.byref(ns),
+                                   C.cast(cb, C.c_void_p), None))
+    return e.value, int(ns.value), int(occ.value)
 
 
 def contract(a: List[BTensor], b: List[BTensor], obs: Optional[List[BTensor]] = None) -> float:

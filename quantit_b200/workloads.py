@@ -256,3 +256,91 @@ def hubbard_theta(D: int, rng: np.random.Generator, n_filling: int = 10):
     right = bond2d(D, n_filling + 2)  # the two sites add between 0 and 4 particles: centre the right bond on +2
     return rand_like(shape([beta, HUBBARD_SITE, HUBBARD_SITE, conj_leg(right)], (0, 0)), rng)
 
+
+# ---- Heisenberg model on an arbitrary bond list as a U(1) MPO (BASELINE.json configs[3]: width-6 cylinder) -----------------
+def heisenberg_bonds_mpo(L: int, bonds, Jp: float = 0.25):
+    """H = sum_{(i,j) in bonds} Jp (2 S+_i S-_j + 2 S-_i S+_j + Sz_i Sz_j) in the convention of heisenberg_W (Pauli-like
+    matrices sz = diag(1,-1), up, dn; the nearest-neighbour chain gives heisenberg_mpo). Finite-state-machine MPO on the
+    1-D ordering 0..L-1: MPO bond k (between sites k-1 and k) carries the states `done` (charge 0), one state per pending
+    half-bond (i, a) with i < k <= j_max(i), a in {up: charge +2, dn: -2, sz: 0}, and `start` (charge 0); a pending
+    operator is shared by every bond (i, j) that starts at i. Every state is a section of size 1 (the reference's
+    bMPO::coalesce / qtb_coalesce merges equal charges). Returns L site tensors W[wl, s', wr, s] like heisenberg_mpo."""
+    sz = np.diag([1.0, -1.0])
+    up = np.array([[0.0, 1.0], [0.0, 0.0]])
+    dn = up.T
+    ident = np.eye(2)
+    ops = {"up": up, "dn": dn, "sz": sz}
+    partner = {"up": (dn, 2 * Jp), "dn": (up, 2 * Jp), "sz": (sz, Jp)}
+    charge = {"up": 2, "dn": -2, "sz": 0}
+    ends = {}
+    for (i, j) in bonds:
+        i, j = (i, j) if i < j else (j, i)
+        assert 0 <= i < j < L
+        ends.setdefault(i, set()).add(j)
+
+    def states(k):  # MPO bond k
+        if k == 0:
+            return [("start",)]
+        if k == L:
+            return [("done",)]
+        st = [("done",)]
+        for i in sorted(ends):
+            if i < k <= max(ends[i]):
+                st += [(i, a) for a in ("up", "dn", "sz")]
+        return st + [("start",)]
+
+    def q(state):
+        return (0,) if len(state) == 1 else (charge[state[1]],)
+
+    sites = []
+    for k in range(L):
+        sl, sr = states(k), states(k + 1)
+        lb = ([1] * len(sl), [q(t) for t in sl])
+        rb = ([1] * len(sr), [q(t) for t in sr])
+        sh = shape([lb, SPIN_HALF, conj_leg(rb), conj_leg(SPIN_HALF)], (0,))
+        dense = np.zeros((len(sl), 2, len(sr), 2))
+        ri = {t: n for n, t in enumerate(sr)}
+        for a_, t in enumerate(sl):
+            if t == ("done",):
+                dense[a_, :, ri[("done",)], :] += ident
+            elif t == ("start",):
+                if ("start",) in ri:
+                    dense[a_, :, ri[("start",)], :] += ident
+                for a in ("up", "dn", "sz"):
+                    if (k, a) in ri:
+                        dense[a_, :, ri[(k, a)], :] += ops[a]
+            else:
+                i, a = t
+                if k in ends[i]:
+                    op, c = partner[a]
+                    dense[a_, :, ri[("done",)], :] += c * op
+                if t in ri:
+                    dense[a_, :, ri[t], :] += ident
+        out = dict(sh)
+        out["blocks"] = {}
+        for idx in allowed_indices(sh):
+            if dense[idx] != 0.0:
+                out["blocks"][idx] = np.full((1, 1, 1, 1), dense[idx])
+        assert len(out["blocks"]) == np.count_nonzero(dense), "an MPO element violates the U(1) selection rule"
+        sites.append(out)
+    return sites
+
+
+def cylinder_bonds(Lx: int, Ly: int):
+    """nearest-neighbour bonds of an Lx x Ly square lattice, periodic around the circumference Ly (a cylinder), open along
+    Lx; site (x, y) -> x * Ly + y (column-major snake-free ordering, the one of the reference's 4x8 fixture)"""
+    b = []
+    for x in range(Lx):
+        for y in range(Ly):
+            s = x * Ly + y
+            if Ly > 2 or y == 0:
+                b.append((s, x * Ly + (y + 1) % Ly)) if Ly > 1 else None
+            if x + 1 < Lx:
+                b.append((s, (x + 1) * Ly + y))
+    return sorted(set((min(i, j), max(i, j)) for i, j in b if i != j))
+
+
+def heisenberg_cylinder_mpo(Lx: int, Ly: int = 6, Jp: float = 0.25):
+    """BASELINE.json configs[3]: the width-`Ly` Heisenberg cylinder (the reference ships only the 4x8 fixture files)"""
+    return heisenberg_bonds_mpo(Lx * Ly, cylinder_bonds(Lx, Ly), Jp)
+

@@ -156,3 +156,56 @@ def test_large_bond_update_and_svd_inside_a_real_run(engine, tmp_path):
     got = back(new)
     assert orc.same_structure(got, rpsi)
     assert orc.max_rel_err(got, rpsi) <= 1e-10
+
+
+def test_dmrg_from_last_site_centre_and_logger_callback(engine):
+    """reference dmrg_impl accepts an orthogonality centre on the last site (dmrg.cpp:229-233: stepped back by one without
+    regauging) and reports every sweep to a dmrg_logger while the run is in progress (dmrg_logger.h)"""
+    qb = engine
+    from quantit_b200 import workloads as wl
+    L = 10
+    H = [qb.BTensor.from_host(**h) for h in wl.heisenberg_mpo(L)]
+    mk = lambda: [qb.BTensor.from_host(**p_) for p_ in wl.random_mps(L, 4, L % 2, seed=3)]
+    opts = qb.dmrg_options(1e-12, 1e-11, 32, 4, 40)
+    psi0 = mk()
+    E0 = qb.dmrg(H, psi0, opts, oc=0)
+    psi1 = mk()
+    oc = qb.move_oc(psi1, 0, L - 1)
+    assert oc == L - 1
+    seen = []
+    E1, nsw, oc_out = qb.dmrg_logged(H, psi1, opts, lambda it, e, secs, bonds: seen.append((it, e, len(bonds))), oc=L - 1)
+    assert oc_out == L - 2
+    assert len(seen) == nsw and seen[-1][0] == nsw - 1 and seen[-1][2] == L + 1
+    assert abs(seen[-1][1] - E1) <= 1e-12 * abs(E1)
+    assert abs(E1 - E0) <= 1e-8 * abs(E0)  # the same ground state from either end
+    assert abs(qb.contract(psi1, psi1, H) / qb.contract(psi1, psi1) - E1) <= 1e-8 * abs(E1)
+
+
+def test_width6_cylinder_against_exact_diagonalisation(engine):
+    """BASELINE.json configs[3] in miniature: Heisenberg cylinder of circumference 6 (2 x 6 = 12 sites, MPO bond up to 20
+    sections before coalescing), U(1) two-site DMRG at a bond dimension that is exact for 12 sites, against the lowest
+    eigenvalue of the dense Hamiltonian in the Sz = 0 sector"""
+    qb = engine
+    from quantit_b200 import workloads as wl
+    Lx, Ly = 2, 6
+    L = Lx * Ly
+    H_sites = wl.heisenberg_cylinder_mpo(Lx, Ly)
+    H = [qb.BTensor.from_host(**h) for h in H_sites]
+    H = qb.coalesce(H, 1e-12)  # merge the equal-charge MPO states like the reference's bMPO::coalesce
+    psi = [qb.BTensor.from_host(**p_) for p_ in wl.random_mps(L, 8, 0, seed=1)]
+    E = qb.dmrg(H, psi, qb.dmrg_options(1e-14, 1e-12, 64, 4, 60), oc=0)
+    # dense reference restricted to Sz = 0
+    sz, up, I = np.diag([1.0, -1.0]), np.array([[0.0, 1.0], [0.0, 0.0]]), np.eye(2)
+    dn = up.T
+
+    def op(o, i):
+        m = np.array([[1.0]])
+        for k in range(L):
+            m = np.kron(m, o if k == i else I)
+        return m
+    Hd = sum(0.25 * (2 * op(up, i) @ op(dn, j) + 2 * op(dn, i) @ op(up, j) + op(sz, i) @ op(sz, j))
+             for i, j in wl.cylinder_bonds(Lx, Ly))
+    mag = sum(np.diag(op(sz, i)) for i in range(L))
+    keep = np.where(mag == 0)[0]
+    E_exact = np.linalg.eigvalsh(Hd[np.ix_(keep, keep)])[0]
+    assert abs(E - E_exact) <= 1e-9 * abs(E_exact), (E, E_exact)

@@ -1,5 +1,6 @@
 """CPU tests of the host-side logic: workload generators and the QTBT exchange format."""
 import numpy as np
+import pytest
 
 import qtb_oracle as orc
 from quantit_b200 import workloads as wl
@@ -51,3 +52,43 @@ def test_chain_generators_feed_a_valid_dmrg():
             keys = sorted(key for key in t["blocks"] if key[0] == ql)
             M = np.concatenate([t["blocks"][key].reshape(t["blocks"][key].shape[0], -1) for key in keys], axis=1)
             assert np.allclose(M @ M.T, np.eye(M.shape[0]), atol=1e-12)
+
+
+def _dense_from_mpo(sites):
+    def dense_site(s):
+        D = np.zeros((len(s["sec_sizes"][0]), 2, len(s["sec_sizes"][2]), 2))
+        for idx, v in s["blocks"].items():
+            D[idx] = v.reshape(())
+        return D
+    M = dense_site(sites[0])[0].transpose(1, 0, 2)  # [wr, s', s]
+    for k in range(1, len(sites)):
+        W = dense_site(sites[k])
+        M = np.einsum("wab,wcxd->xacbd", M, W).reshape(W.shape[2], M.shape[1] * 2, M.shape[2] * 2)
+    return M[0]
+
+
+def _dense_heisenberg(L, bonds, Jp):
+    sz, up, I = np.diag([1.0, -1.0]), np.array([[0.0, 1.0], [0.0, 0.0]]), np.eye(2)
+    dn = up.T
+
+    def op(o, i):
+        m = np.array([[1.0]])
+        for k in range(L):
+            m = np.kron(m, o if k == i else I)
+        return m
+    return sum(Jp * (2 * op(up, i) @ op(dn, j) + 2 * op(dn, i) @ op(up, j) + op(sz, i) @ op(sz, j)) for i, j in bonds)
+
+
+@pytest.mark.parametrize("Lx,Ly", [(3, 3), (2, 4), (4, 2)])
+def test_cylinder_mpo_is_the_heisenberg_hamiltonian(Lx, Ly):
+    """the finite-state-machine U(1) MPO of workloads.heisenberg_bonds_mpo (BASELINE.json configs[3] generator) against
+    the Hamiltonian built term by term"""
+    from quantit_b200 import workloads as wl
+    bonds = wl.cylinder_bonds(Lx, Ly)
+    assert np.abs(_dense_from_mpo(wl.heisenberg_cylinder_mpo(Lx, Ly)) - _dense_heisenberg(Lx * Ly, bonds, 0.25)).max() == 0.0
+
+
+def test_bond_list_mpo_reduces_to_the_chain():
+    from quantit_b200 import workloads as wl
+    chain = wl.heisenberg_bonds_mpo(6, [(i, i + 1) for i in range(5)])
+    assert np.abs(_dense_from_mpo(chain) - _dense_from_mpo(wl.heisenberg_mpo(6))).max() == 0.0
