@@ -22,6 +22,7 @@ Ctx::~Ctx()
 {
 	ctx_destroy_nccl(*this);
 	plan_cache.clear();
+	plan_slab.reset();
 	trim_cache();
 	for (Arena *a : arenas) // tensors that outlive the context: their arenas are orphaned, the blocks released below
 		a->ctx = nullptr;
@@ -31,6 +32,9 @@ Ctx::~Ctx()
 	live_blocks.clear();
 	if (ring_base)
 		cudaFreeHost(ring_base);
+	for (auto ev : ring_event)
+		if (ev)
+			cudaEventDestroy(ev);
 	if (pinned)
 		cudaFreeHost(pinned);
 	if (pinned_gauge_)
@@ -151,13 +155,15 @@ void ctx_free(Ctx &ctx, void *p)
 
 // Small structure tables go through a pinned ring (owned by the context) so that the copy is truly asynchronous; the
 // ring is only recycled after a stream synchronisation.
-void *ctx_upload(Ctx &ctx, const void *host, size_t bytes)
+// host -> device copy of a small table through the pinned ring (truly asynchronous). The ring is cut into kRingParts
+// parts, each closed by an event when the write position leaves it; a part is reused only after ITS event has completed
+// — the copies that read it are done — instead of draining the whole stream.
+void ctx_stage_copy(Ctx &ctx, void *d, const void *host, size_t bytes)
 {
-	void *d = ctx_alloc(ctx, bytes);
 	if (bytes == 0)
-		return d;
+		return;
 	const size_t need = (bytes + 255) & ~size_t(255);
-	if (ctx.ring_base == nullptr || need > ctx.ring_size)
+	if (ctx.ring_base == nullptr || need * Ctx::kRingParts > ctx.ring_size)
 	{
 		if (ctx.ring_base)
 		{
@@ -165,19 +171,40 @@ void *ctx_upload(Ctx &ctx, const void *host, size_t bytes)
 			cudaFreeHost(ctx.ring_base);
 			ctx.ring_base = nullptr;
 		}
-		ctx.ring_size = std::max<size_t>(need * 2, size_t(16) << 20);
+		ctx.ring_size = std::max<size_t>(need * 2 * Ctx::kRingParts, size_t(64) << 20);
 		QTB_CUDA(cudaMallocHost((void **)&ctx.ring_base, ctx.ring_size));
 		ctx.ring_pos = 0;
+		ctx.ring_part = 0;
+		for (int k = 0; k < Ctx::kRingParts; ++k)
+		{
+			if (!ctx.ring_event[k])
+				QTB_CUDA(cudaEventCreateWithFlags(&ctx.ring_event[k], cudaEventDisableTiming));
+			ctx.ring_busy[k] = false;
+		}
 	}
-	if (ctx.ring_pos + need > ctx.ring_size)
-	{
-		QTB_CUDA(cudaStreamSynchronize(ctx.stream));
-		ctx.ring_pos = 0;
+	const size_t part_size = (ctx.ring_size / Ctx::kRingParts) & ~size_t(255);
+	if (ctx.ring_pos + need > (size_t)(ctx.ring_part + 1) * part_size)
+	{ // leave this part: close it with an event, move to the start of the next one
+		QTB_CUDA(cudaEventRecord(ctx.ring_event[ctx.ring_part], ctx.stream));
+		ctx.ring_busy[ctx.ring_part] = true;
+		ctx.ring_part = (ctx.ring_part + 1) % Ctx::kRingParts;
+		ctx.ring_pos = (size_t)ctx.ring_part * part_size;
+		if (ctx.ring_busy[ctx.ring_part])
+		{
+			QTB_CUDA(cudaEventSynchronize(ctx.ring_event[ctx.ring_part]));
+			ctx.ring_busy[ctx.ring_part] = false;
+		}
 	}
 	std::memcpy(ctx.ring_base + ctx.ring_pos, host, bytes);
 	QTB_CUDA(cudaMemcpyAsync(d, ctx.ring_base + ctx.ring_pos, bytes, cudaMemcpyHostToDevice, ctx.stream));
 	ctx.ring_pos += need;
 	ctx.counters[4] += (i64)bytes;
+}
+
+void *ctx_upload(Ctx &ctx, const void *host, size_t bytes)
+{
+	void *d = ctx_alloc(ctx, bytes);
+	ctx_stage_copy(ctx, d, host, bytes);
 	return d;
 }
 
@@ -207,14 +234,27 @@ static inline uint64_t mix64(uint64_t h, uint64_t v)
 	return h;
 }
 
-Plan::~Plan()
+Plan::~Plan() {} // the tables live in PlanSlabs (released with the last plan that uses them)
+
+// device copy of a plan table: carved from the context's current slab, uploaded through the pinned ring
+void ctx_stage_copy(Ctx &ctx, void *d, const void *host, size_t bytes);
+static void *plan_upload(Ctx &ctx, Plan &plan, const void *host, size_t bytes)
 {
-	if (d_blob && ctx)
-		ctx_free(*ctx, d_blob);
-	if (ctx)
-		for (auto &kv : owned)
-			if (kv.second.d_tiles)
-				ctx_free(*ctx, kv.second.d_tiles);
+	constexpr size_t kSlab = size_t(32) << 20;
+	const size_t need = (bytes + 255) & ~size_t(255);
+	if (!ctx.plan_slab || ctx.plan_slab->used + need > ctx.plan_slab->size)
+	{
+		auto slab = std::make_shared<PlanSlab>();
+		slab->size = std::max(kSlab, need);
+		QTB_CUDA(cudaMalloc((void **)&slab->base, slab->size));
+		ctx.plan_slab = slab;
+	}
+	void *d = ctx.plan_slab->base + ctx.plan_slab->used;
+	ctx.plan_slab->used += need;
+	if (plan.slabs.empty() || plan.slabs.back() != ctx.plan_slab)
+		plan.slabs.push_back(ctx.plan_slab);
+	ctx_stage_copy(ctx, d, host, bytes);
+	return d;
 }
 
 // =====================================================================================================================
@@ -291,6 +331,18 @@ std::vector<int32_t> schedule_tiles(std::vector<GemmTile> &tiles, std::vector<do
 	return begin;
 }
 
+std::vector<int32_t> skinny_item_prefix(const std::vector<GemmTile> &tiles)
+{ // streaming (MPO) kernel: prefix sums of the number of kSkinnyRows-row work items of every block record
+	std::vector<int32_t> p(tiles.size() + 1, 0);
+	for (size_t t = 0; t < tiles.size(); ++t)
+	{
+		const i64 items = ((i64)tiles[t].M + kSkinnyRows - 1) / kSkinnyRows;
+		QTB_REQUIRE((i64)p[t] + items < (i64(1) << 31), QTB_ERR_INVALID_ARGUMENT, "too many work items in one contraction");
+		p[t + 1] = p[t] + (int32_t)items;
+	}
+	return p;
+}
+
 std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world)
 { // longest processing time first: heaviest section to the least loaded rank; ties -> lower section / lower rank
 	const size_t n = weights.size();
@@ -352,12 +404,12 @@ static const Plan::Owned &owned_tiles(Ctx &ctx, const std::shared_ptr<Plan> &pla
 		if (!mine.empty())
 		{
 			ow.ncta = std::max(1, std::min<int>(ow.ntiles, gemm_grid_limit(ctx, plan->tile_cfg)));
-			const auto cb = schedule_tiles(mine, cost, ow.ncta);
+			const auto cb = plan->tile_cfg == 2 ? skinny_item_prefix(mine) : schedule_tiles(mine, cost, ow.ncta);
 			const size_t tb = (mine.size() * sizeof(GemmTile) + 15) & ~size_t(15);
 			std::vector<char> blob(tb + cb.size() * sizeof(int32_t));
 			std::memcpy(blob.data(), mine.data(), mine.size() * sizeof(GemmTile));
 			std::memcpy(blob.data() + tb, cb.data(), cb.size() * sizeof(int32_t));
-			ow.d_tiles = (GemmTile *)ctx_upload(ctx, blob.data(), blob.size());
+			ow.d_tiles = (GemmTile *)plan_upload(ctx, *plan, blob.data(), blob.size());
 			ow.d_cta_begin = (int32_t *)((char *)ow.d_tiles + tb);
 		}
 		it = plan->owned.emplace(h, ow).first;
@@ -833,6 +885,16 @@ std::vector<int32_t> flat_offsets(const Tensor &t, i64 b, const std::vector<i64>
 static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const std::vector<i64> &dims_a_in,
                                         const std::vector<i64> &dims_b_in)
 {
+	// QTB_PROFILE >= 3: where the host time of a plan goes (accumulated per context, printed by prof_dump)
+	auto tp0 = std::chrono::steady_clock::now();
+	auto lap = [&](int slot)
+	{
+		if (ctx.prof_level < 3)
+			return;
+		auto now = std::chrono::steady_clock::now();
+		ctx.plan_phase_ms[slot] += std::chrono::duration<double, std::milli>(now - tp0).count();
+		tp0 = now;
+	};
 	// ---- validation: reference compute_tdot_shape + check_product_compat<true>, btensor.cpp:841-883,783-825 ----
 	QTB_REQUIRE(dims_a_in.size() == dims_b_in.size(), QTB_ERR_CHECK,
 	            "both dimension lists should have the same length.");
@@ -902,6 +964,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 		push_dim(b, d);
 	out.st.finalize();
 
+	lap(0);
 	// ---- block-pair matching: reference two-pointer merge over "columns", btensor.cpp:2057-2108 ----
 	// Equivalent formulation: every (A block, B block) pair with equal contracted block indices, grouped by the output
 	// index (freeA, freeB) in ascending order, pairs inside a group in ascending contracted index.
@@ -944,6 +1007,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	std::sort(cands.begin(), cands.end(),
 	          [](const Cand &x, const Cand &y) { return x.okey != y.okey ? x.okey < y.okey : x.ckey < y.ckey; });
 
+	lap(1);
 	// ---- operand offset tables (the fused permute_bl, btensor.cpp:1843-1894) ----
 	struct OpTab
 	{
@@ -1126,6 +1190,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	}
 	out.compute_hash();
 
+	lap(2);
 	// ---- tiling ----
 	auto count_tiles = [&](int bm, int bn, double &padded)
 	{
@@ -1185,12 +1250,12 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			nchunks += (plan->pairs[p].K + BKc - 1) / BKc;
 			ksum += plan->pairs[p].K;
 		}
-		for (int m0 = 0; m0 < o.M; m0 += bm)
+		for (int m0 = 0; m0 < o.M; m0 += (plan->tile_cfg == 2 ? std::max(o.M, 1) : bm))
 			for (int n0 = 0; n0 < o.N; n0 += bn)
 			{
 				double c;
-				if (plan->tile_cfg == 2)
-					c = 200.0 + (double)std::min<i64>(bm, o.M - m0) / 256.0 * (double)ksum * (4.0 + o.N);
+				if (plan->tile_cfg == 2) // ONE record per output block: the kernel cuts it into kSkinnyRows-row work items itself
+					c = 200.0 + (double)o.M / 256.0 * (double)ksum * (4.0 + o.N);
 				else
 				{
 					// the busiest consumer warp of a tile always computes its whole warp tile (unpredicated path)
@@ -1214,11 +1279,12 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			t.shf0 = 0;
 	}
 	plan->ncta = std::max(1, std::min<int>((int)plan->tiles.size(), gemm_grid_limit(ctx, plan->tile_cfg)));
-	if (plan->tile_cfg == 2) // the skinny kernel walks the list grid-stride: items are uniform, no static schedule needed
-		plan->cta_begin.assign(1, 0);
+	if (plan->tile_cfg == 2)
+		plan->cta_begin = skinny_item_prefix(plan->tiles); // work-item prefix sums: item w belongs to the block t with prefix[t] <= w
 	else
 		plan->cta_begin = schedule_tiles(plan->tiles, plan->tile_cost, plan->ncta);
 
+	lap(3);
 	// ---- upload ----
 	auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
 	const size_t s_outs = align(plan->outs.size() * sizeof(GemmOut));
@@ -1233,7 +1299,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	std::memcpy(blob.data() + s_outs + s_pairs + align(plan->tiles.size() * sizeof(GemmTile)), plan->cta_begin.data(),
 	            plan->cta_begin.size() * sizeof(int32_t));
 	std::memcpy(blob.data() + s_outs + s_pairs + s_tiles, plan->offpool.data(), plan->offpool.size() * sizeof(int32_t));
-	plan->d_blob = ctx_upload(ctx, blob.data(), total);
+	plan->d_blob = plan_upload(ctx, *plan, blob.data(), total);
 	char *base = (char *)plan->d_blob;
 	plan->d_outs = (GemmOut *)base;
 	plan->d_pairs = (GemmPair *)(base + s_outs);
@@ -1242,6 +1308,7 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	plan->d_offpool = (int32_t *)(base + s_outs + s_pairs + s_tiles);
 	plan->d_counter = (int *)(base + s_outs + s_pairs + s_tiles + s_pool);
 	ctx.counters[2] += 1;
+	lap(4);
 	return plan;
 }
 
@@ -1279,6 +1346,13 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 void Ctx::prof_dump(const char *title)
 {
 	std::fprintf(stderr, "[qtb profile] %s\n", title);
+	if (prof_level >= 3)
+	{
+		std::fprintf(stderr, "[qtb profile]   plan phases (ms): validate+structure %.1f, matching %.1f, pairs+tables %.1f, tiling+schedule %.1f, upload %.1f\n",
+		             plan_phase_ms[0], plan_phase_ms[1], plan_phase_ms[2], plan_phase_ms[3], plan_phase_ms[4]);
+		for (double &v : plan_phase_ms)
+			v = 0;
+	}
 	for (auto &kv : prof)
 		std::fprintf(stderr, "[qtb profile]   %-28s calls %6ld built %5ld plan %9.2f ms gemm %9.2f ms  %8.3f GFLOP  %7.2f TFLOP/s tiles %ld\n",
 		             kv.first.c_str(), (long)kv.second.calls, (long)kv.second.built, kv.second.plan_ms, kv.second.gemm_ms,

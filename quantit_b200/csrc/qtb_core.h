@@ -189,6 +189,20 @@ static_assert(sizeof(GemmPair) == 64, "GemmPair is uploaded as a packed 64-byte 
 
 constexpr int kSkinnyRows = 1024; // rows of an output block per work item of the skinny (MPO) contraction kernel
 
+// Plan tables live in large device slabs carved linearly (a cudaMalloc per plan — ~1000 plans per saturated sweep, no
+// two of the same size — cost 0.2 ms each and was the largest part of the planner's host time); a slab goes back to the
+// driver when the last plan that points into it is destroyed.
+struct PlanSlab
+{
+	char *base = nullptr;
+	size_t size = 0, used = 0;
+	~PlanSlab()
+	{
+		if (base)
+			cudaFree(base);
+	}
+};
+
 struct Plan
 {
 	// output layout
@@ -224,6 +238,7 @@ struct Plan
 		i64 flops = 0;
 	};
 	std::unordered_map<uint64_t, Owned> owned;
+	std::vector<std::shared_ptr<PlanSlab>> slabs; // keep the slabs of d_blob and of the owned tile lists alive
 	std::vector<i64> out_flops; // [out blocks] 2 M N sum K
 	~Plan();
 };
@@ -238,12 +253,17 @@ struct Ctx
 	int sm_count = 148;
 	i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	std::unordered_map<uint64_t, std::shared_ptr<Plan>> plan_cache;
+	std::shared_ptr<PlanSlab> plan_slab; // the slab new plan tables are carved from
 	// live arenas: a context that is destroyed before its tensors orphans them (Arena::ctx = nullptr, the device block is
 	// released with the context) so that a late qtb_tensor_free is harmless
 	std::unordered_set<Arena *> arenas;
 	// pinned ring for small asynchronous uploads (plan tables, descriptors), recycled after a stream synchronisation
+	static constexpr int kRingParts = 4;
 	char *ring_base = nullptr;
 	size_t ring_size = 0, ring_pos = 0;
+	int ring_part = 0;
+	cudaEvent_t ring_event[kRingParts] = {nullptr, nullptr, nullptr, nullptr};
+	bool ring_busy[kRingParts] = {false, false, false, false};
 	// kernels whose function attributes (dynamic shared memory opt-in, carve-out) were set for this context's device
 	uint32_t kernel_attr_mask = 0;
 	bool attr_once(int bit)
@@ -276,6 +296,7 @@ struct Ctx
 		double plan_ms = 0, gemm_ms = 0;
 	};
 	std::map<std::string, ProfRec> prof;
+	double plan_phase_ms[5] = {0, 0, 0, 0, 0};
 	void prof_dump(const char *title);
 	// charge-sector sharding (qtb_ctx_set_sharding)
 	int rank = 0, world = 1;
@@ -324,6 +345,7 @@ std::vector<int32_t> schedule_tiles(std::vector<GemmTile> &tiles, std::vector<do
 int gemm_grid_limit(const Ctx &ctx, int tile_cfg); // CTAs the grouped GEMM keeps resident (SM count x CTAs per SM)
 // sharding helpers (qtb_core.cpp)
 std::vector<int32_t> lpt_assign(const std::vector<double> &weights, int world);
+std::vector<int32_t> skinny_item_prefix(const std::vector<GemmTile> &tiles);
 // one step of a sharded chain of contractions: computes only the output blocks whose section along `owner_dim` belongs
 // to this rank (the rest of the freshly allocated arena is zero); `owner` maps sections of that dim to ranks.
 // zero_rest: clear the whole output arena first (needed when the result is summed over the ranks; an intermediate of a

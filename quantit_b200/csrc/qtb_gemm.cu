@@ -530,6 +530,7 @@ constexpr int kSkinnyBatch = 32;            // pair descriptors staged in shared
 
 template <int NMAX>
 __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(const GemmTile *__restrict__ tiles, int ntiles,
+                                                           const int32_t *__restrict__ item_prefix,
                                                            const GemmPair *__restrict__ pairs,
                                                            const int32_t *__restrict__ offpool,
                                                            const double *__restrict__ A, const double *__restrict__ B,
@@ -538,9 +539,21 @@ __global__ void __launch_bounds__(256, (NMAX <= 4 ? 4 : 1)) skinny_gemm_kernel(c
 	constexpr int R = kSkinnyR;
 	__shared__ GemmPair sp[kSkinnyBatch];
 	static_assert(sizeof(GemmPair) % 4 == 0, "descriptor copied as words");
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+	const int nitems = item_prefix[ntiles];
+	for (int w = blockIdx.x; w < nitems; w += gridDim.x)
 	{
-		const GemmTile ob = tiles[t];
+		// work item w = chunk (w - prefix[t]) of block record t: binary search of the prefix sums (block-uniform)
+		int lo = 0, hi = ntiles;
+		while (hi - lo > 1)
+		{
+			const int mid = (lo + hi) >> 1;
+			if (item_prefix[mid] <= w)
+				lo = mid;
+			else
+				hi = mid;
+		}
+		GemmTile ob = tiles[lo];
+		ob.m0 = (w - item_prefix[lo]) * kSkinnyRows;
 		const GemmTile &tile = ob;
 		const int M = ob.M, N = ob.N;
 		int m[R];
@@ -638,11 +651,11 @@ void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const doub
 	            "the fused linear-combination epilogue is not available on the streaming (MPO) kernel");
 	if (plan.tile_cfg == 2)
 	{
-		const int grid = std::min(ntiles, ctx.sm_count * 8);
+		const int grid = ctx.sm_count * 8; // grid-stride over the work items (their count lives in the prefix array)
 		if (plan.max_n <= 4)
-			skinny_gemm_kernel<4><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_pairs, plan.d_offpool, a, b, c);
+			skinny_gemm_kernel<4><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, d_cta_begin, plan.d_pairs, plan.d_offpool, a, b, c);
 		else
-			skinny_gemm_kernel<kSkinnyN><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, plan.d_pairs,
+			skinny_gemm_kernel<kSkinnyN><<<grid, 256, 0, ctx.stream>>>(d_tiles, ntiles, d_cta_begin, plan.d_pairs,
 			                                                            plan.d_offpool, a, b, c);
 		QTB_CUDA(cudaGetLastError());
 	}
