@@ -204,6 +204,50 @@ __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned sme
 	}
 }
 
+// Consumer side: the DMMAs of one staged K chunk for one warp tile, with the operand layouts as template parameters.
+// With run-time strides (first version) every fragment load cost an IMAD + IADD and the address registers left room
+// for ONE live B fragment: ptxas emitted LDS -> 4 DMMA -> LDS -> 4 DMMA ..., each group waiting out the shared-memory
+// latency (ncu source view of configs[1], profiles/r2: the short-scoreboard samples sit on the DMMA after every LDS,
+// tensor pipe 44 % active). Here every offset is an immediate and the fragments of k-step kk + 1 are requested before
+// the 16 (32) DMMAs of k-step kk issue.
+template <class Cfg, bool AKC, bool BNC>
+__device__ __forceinline__ void mma_chunk(double (&acc)[Cfg::WM / 8][Cfg::WN / 8][2], const double *__restrict__ As,
+                                          const double *__restrict__ Bs, int wm0, int wn0, int g, int q, int shA, int shB)
+{
+	constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, PAD = Cfg::kPad;
+	constexpr int MI = Cfg::WM / 8, NI = Cfg::WN / 8;
+	constexpr int sa_m = AKC ? (BK + PAD) : 1, sa_k = AKC ? 1 : (BM + PAD);
+	constexpr int sb_k = BNC ? (BN + PAD) : 1, sb_n = BNC ? 1 : (BK + PAD);
+	const double *Ap = As + (wm0 + g) * sa_m + q * sa_k + shA;
+	const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n + shB;
+	double af[2][MI], bf[2][NI];
+#pragma unroll
+	for (int i = 0; i < MI; ++i)
+		af[0][i] = Ap[i * 8 * sa_m];
+#pragma unroll
+	for (int j = 0; j < NI; ++j)
+		bf[0][j] = Bp[j * 8 * sb_n];
+#pragma unroll
+	for (int ks = 0; ks < BK / 4; ++ks)
+	{
+		const int cur = ks & 1, nxt = cur ^ 1;
+		if (ks + 1 < BK / 4)
+		{
+#pragma unroll
+			for (int i = 0; i < MI; ++i)
+				af[nxt][i] = Ap[i * 8 * sa_m + (ks + 1) * 4 * sa_k];
+#pragma unroll
+			for (int j = 0; j < NI; ++j)
+				bf[nxt][j] = Bp[(ks + 1) * 4 * sb_k + j * 8 * sb_n];
+		}
+#pragma unroll
+		for (int i = 0; i < MI; ++i)
+#pragma unroll
+			for (int j = 0; j < NI; ++j)
+				dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+	}
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
     grouped_gemm_kernel(const GemmTile *__restrict__ tiles, const int32_t *__restrict__ cta_begin,
@@ -416,10 +460,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					shf_next = pairs[p + 1].shf & bulk_mask;
 				}
 				const int a_kc = lay & 1, b_nc = lay >> 1;
-				const int sa_m = a_kc ? (BK + PAD) : 1;
-				const int sa_k = a_kc ? 1 : (BM + PAD);
-				const int sb_k = b_nc ? (BN + PAD) : 1;
-				const int sb_n = b_nc ? 1 : (BK + PAD);
 				// one-element shifts of the bulk-staged runs (see the producer): the run index is the fragment row g (A rows /
 				// B columns when k is the unit-stride direction) or the fragment k index q; every other term of the run's
 				// source address (tile origins, chunk origins, warp and MMA offsets) is even
@@ -431,8 +471,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					mbar_wait(full0 + 8 * stage, phase);
 					const double *As = smem + stage * Cfg::kStage;
 					const double *Bs = As + Cfg::kASize;
-					const double *Ap = As + (wm0 + g) * sa_m + q * sa_k + shA;
-					const double *Bp = Bs + q * sb_k + (wn0 + g) * sb_n + shB;
 					// A warp whose 32-row x 32-column (64 x 32 for the large configuration) tile intersects the block
 					// computes ALL of it, unpredicated: rows / columns past the block edge were clamped by the producer
 					// (finite data, never stored) and the K tail is zero-filled. The first version skipped invalid 8x8
@@ -440,22 +478,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					// consumer samples on integer / branch instructions) to save 1.49x -> 1.14x of padded DMMA work.
 					if (any)
 					{
-#pragma unroll
-						for (int kk = 0; kk < BK; kk += 4)
-						{
-							double af[MI], bf[NI];
-#pragma unroll
-							for (int i = 0; i < MI; ++i)
-								af[i] = Ap[i * 8 * sa_m + kk * sa_k];
-#pragma unroll
-							for (int j = 0; j < NI; ++j)
-								bf[j] = Bp[kk * sb_k + j * 8 * sb_n];
-#pragma unroll
-							for (int i = 0; i < MI; ++i)
-#pragma unroll
-								for (int j = 0; j < NI; ++j)
-									dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-						}
+						if (lay == 0)
+							mma_chunk<Cfg, false, false>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+						else if (lay == 1)
+							mma_chunk<Cfg, true, false>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+						else if (lay == 2)
+							mma_chunk<Cfg, false, true>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+						else
+							mma_chunk<Cfg, true, true>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
 					}
 					__syncwarp();
 					if (lane == 0)

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1366,6 +1367,166 @@ __global__ void __launch_bounds__(256) eigh_rayleigh_kernel(const RayleighGroup 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Global truncation on the device (north star: "the global truncation over all sectors' singular values uses a
+// device-wide select"; reference truncate_impl, btensor_linalg.cpp:657-755, compute_last_index, LinearAlgebra.cpp:57-75).
+// The reference copies every singular value to the CPU, sorts them and walks the tail with one .item() per discarded
+// value. Here: a per-sector bitonic sort (descending, ties by column index = the stable order), one device-wide
+// descending sort of all values, the suffix sums of |d|^pow, the reference's stopping rule evaluated in parallel
+// (largest index >= min whose suffix sum exceeds tol^pow and that is < max), the threshold d[last](1 - 2 eps) and the
+// per-sector kept counts (strict >). Only the kept counts (one int per sector) go back to the host, which needs them
+// to allocate U, d, V.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class Less>
+__device__ __forceinline__ void bitonic_sort_shared(int n2, Less less_at)
+{ // in-place bitonic network over n2 (power of two) shared-memory slots; less_at(i, j, ascending) swaps if needed
+	for (int k = 2; k <= n2; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int i = threadIdx.x; i < n2; i += blockDim.x)
+			{
+				const int ixj = i ^ j;
+				if (ixj > i)
+					less_at(i, ixj, (i & k) == 0);
+			}
+			__syncthreads();
+		}
+}
+
+// one CTA per sector: perm[sig_off + j] = column with the j-th largest sigma; sorted[sig_off + j] = that sigma
+__global__ void __launch_bounds__(1024) svd_sector_sort_kernel(const SvdGroup *__restrict__ groups, const int *__restrict__ sig_off,
+                                                                const double *__restrict__ sigma, int *__restrict__ perm,
+                                                                double *__restrict__ sorted)
+{
+	extern __shared__ double ss_key[];
+	const SvdGroup G = groups[blockIdx.x];
+	int n2 = 1;
+	while (n2 < G.n)
+		n2 <<= 1;
+	int *ss_idx = reinterpret_cast<int *>(ss_key + n2);
+	const int off = sig_off[blockIdx.x];
+	for (int i = threadIdx.x; i < n2; i += blockDim.x)
+	{
+		ss_key[i] = i < G.n ? sigma[off + i] : -1.0; // sigma >= 0: the padding sorts last
+		ss_idx[i] = i;
+	}
+	__syncthreads();
+	bitonic_sort_shared(n2,
+	                    [&](int a, int b, bool first_goes_first)
+	                    { // order: larger sigma first, equal sigma by smaller column index (stable descending sort)
+		                    const double ka = ss_key[a], kb = ss_key[b];
+		                    const int ia = ss_idx[a], ib = ss_idx[b];
+		                    const bool a_before_b = ka > kb || (ka == kb && ia < ib);
+		                    if (a_before_b != first_goes_first)
+		                    {
+			                    ss_key[a] = kb;
+			                    ss_key[b] = ka;
+			                    ss_idx[a] = ib;
+			                    ss_idx[b] = ia;
+		                    }
+	                    });
+	for (int i = threadIdx.x; i < G.n; i += blockDim.x)
+	{
+		perm[off + i] = ss_idx[i];
+		sorted[off + i] = ss_key[i];
+	}
+}
+
+// one CTA: device-wide select. out[0] = last index (compute_last_index), out[1 + g] = kept count of sector g
+__global__ void __launch_bounds__(1024) svd_select_kernel(const SvdGroup *__restrict__ groups, const int *__restrict__ sig_off,
+                                                           int ngroups, const double *__restrict__ sorted, int total, double tol,
+                                                           double pw, long long min_size, long long max_size,
+                                                           int *__restrict__ out, double *__restrict__ thr_out)
+{
+	extern __shared__ double sv[];
+	__shared__ double s_part[1024];
+	__shared__ int s_last[32];
+	__shared__ double s_thr;
+	int n2 = 1;
+	while (n2 < total)
+		n2 <<= 1;
+	for (int i = threadIdx.x; i < n2; i += blockDim.x)
+		sv[i] = i < total ? sorted[i] : -1.0;
+	__syncthreads();
+	bitonic_sort_shared(n2,
+	                    [&](int a, int b, bool first_goes_first)
+	                    {
+		                    const double ka = sv[a], kb = sv[b];
+		                    if ((ka > kb) != first_goes_first && ka != kb)
+		                    {
+			                    sv[a] = kb;
+			                    sv[b] = ka;
+		                    }
+	                    });
+	// suffix sums S_i = sum_{k >= i} |v_k|^pow: every thread owns a contiguous chunk (summed from the tail), the chunk
+	// totals are scanned from the tail by thread 0 (<= 1024 terms), then every thread revisits its chunk
+	const int chunk = (total + blockDim.x - 1) / blockDim.x;
+	const int lo = min(total, (int)threadIdx.x * chunk), hi = min(total, lo + chunk);
+	auto wgt = [&](double v) { return pw == 2.0 ? v * v : pow(fabs(v), pw); };
+	double acc = 0.0;
+	for (int i = hi - 1; i >= lo; --i)
+		acc += wgt(sv[i]);
+	s_part[threadIdx.x] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		double run = 0.0;
+		for (int t = blockDim.x - 1; t >= 0; --t)
+		{ // s_part[t] <- sum of the chunks strictly after chunk t
+			const double mine = s_part[t];
+			s_part[t] = run;
+			run += mine;
+		}
+	}
+	__syncthreads();
+	const double toln = pow(tol, pw);
+	int best = -1; // largest index >= min_size with S > tol^pow and index < max_size
+	double run = s_part[threadIdx.x];
+	for (int i = hi - 1; i >= lo; --i)
+	{
+		run += wgt(sv[i]);
+		if (i >= min_size && run > toln && (max_size < 0 || i < max_size) && i > best)
+			best = i;
+	}
+	for (int o = 16; o > 0; o >>= 1)
+		best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+	if ((threadIdx.x & 31) == 0)
+		s_last[threadIdx.x >> 5] = best;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		int last = -1;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+			last = max(last, s_last[w]);
+		if (min_size > total - 1)
+			last = total - 1; // the loop of compute_last_index never runs
+		else if (last < 0)
+			last = (int)min_size - 1; // it ran down to the minimum
+		out[0] = last;
+		double thr = last >= 0 ? sv[last] : 0.0;
+		thr -= 2.0 * thr * 2.220446049250313e-16;
+		s_thr = thr;
+		*thr_out = thr;
+	}
+	__syncthreads();
+	const double thr = s_thr;
+	// kept count per sector: leading values strictly above the threshold (lower_bound_impl2, btensor_linalg.cpp:548-558)
+	for (int g = threadIdx.x; g < ngroups; g += blockDim.x)
+	{
+		const double *v = sorted + sig_off[g];
+		int a = 0, b = groups[g].n; // first index with v <= thr (v descending)
+		while (a < b)
+		{
+			const int mid = (a + b) >> 1;
+			if (v[mid] > thr)
+				a = mid + 1;
+			else
+				b = mid;
+		}
+		out[1 + g] = a;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 struct HostGroup
@@ -1639,6 +1800,29 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	SvdGroup *d_groups = nullptr;
 	int *d_sigoff = nullptr;
 	double *d_sigma = nullptr;
+	// truncation select on the device (see svd_select_kernel); the host path remains for eigh (threshold over |e|) and for
+	// inputs beyond one CTA's shared memory
+	i64 cols_all_max = 0;
+	for (i64 g = 0; g < ng; ++g)
+		cols_all_max = std::max<i64>(cols_all_max, dg[g].n);
+	static const bool devsel_env = !(std::getenv("QTB_SVD_DEVSEL") && std::atoi(std::getenv("QTB_SVD_DEVSEL")) == 0);
+	const bool debug_census = std::getenv("QTB_SVD_DEBUG") && std::atoi(std::getenv("QTB_SVD_DEBUG")) >= 2;
+	const bool dev_select = devsel_env && !eigh_mode && ng > 0 && sig_total > 0 && sig_total <= 16384 && cols_all_max <= 8192;
+	int *d_perm_dev = nullptr, *d_sel = nullptr;
+	double *d_sorted = nullptr;
+	std::vector<int> sel_host;
+	// QTB_SVD_DEBUG >= 2: wall-clock split of this call (each mark synchronises the stream)
+	double phase_ms[6] = {0, 0, 0, 0, 0, 0};
+	auto phase_t0 = std::chrono::steady_clock::now();
+	auto mark = [&](int i)
+	{
+		if (!debug_census)
+			return;
+		cudaStreamSynchronize(ctx.stream);
+		const auto t = std::chrono::steady_clock::now();
+		phase_ms[i] += std::chrono::duration<double, std::milli>(t - phase_t0).count();
+		phase_t0 = t;
+	};
 	if (ng > 0)
 	{
 		X = (double *)ctx_alloc(ctx, xtotal * sizeof(double));
@@ -1729,6 +1913,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			ctx_free(ctx, d_em);
 			ctx.counters[0] += 3;
 		}
+		mark(0);
 		// ---- QR preconditioning: F = Q R (blocked Householder), X = [R^T ; I] ----
 		std::vector<i64> qr_order;
 		QrGroup *d_qr = nullptr;
@@ -1809,6 +1994,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			ctx.counters[0] += 1;
 		}
 
+		mark(1);
 		// ---- batched block Jacobi ----
 		{
 			// Ordering: step tau of group g holds the disjoint block pairs (i, j), i < j, with (i + j - 1) mod nb_g == tau.
@@ -2124,6 +2310,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					ctx_free(ctx, L.d_off);
 			}
 		}
+		mark(2);
 		{
 			dim3 grid(64, (unsigned)ng);
 			svd_norm_kernel<<<grid, 128, 0, ctx.stream>>>(d_groups, d_sigoff, X, d_sigma);
@@ -2153,7 +2340,39 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 				QTB_CUDA(cudaGetLastError());
 				ctx_free(ctx, d_qr);
 			}
-			QTB_CUDA(cudaMemcpyAsync(sigma.data(), d_sigma, sig_total * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+			if (dev_select)
+			{
+				d_perm_dev = (int *)ctx_alloc(ctx, (size_t)sig_total * sizeof(int));
+				d_sorted = (double *)ctx_alloc(ctx, (size_t)sig_total * sizeof(double));
+				d_sel = (int *)ctx_alloc(ctx, (size_t)(ng + 1) * sizeof(int) + sizeof(double));
+				int n2max = 1, t2 = 1;
+				while (n2max < cols_all_max)
+					n2max <<= 1;
+				while (t2 < sig_total)
+					t2 <<= 1;
+				if (ctx.attr_once(6))
+				{
+					QTB_CUDA(cudaFuncSetAttribute(svd_sector_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+					QTB_CUDA(cudaFuncSetAttribute(svd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+				}
+				svd_sector_sort_kernel<<<(unsigned)ng, 1024, (size_t)n2max * 12, ctx.stream>>>(d_groups, d_sigoff, d_sigma, d_perm_dev, d_sorted);
+				if (truncate)
+					svd_select_kernel<<<1, 1024, (size_t)t2 * 8, ctx.stream>>>(d_groups, d_sigoff, (int)ng, d_sorted, (int)sig_total, tol, pw,
+					                                                         (long long)min_size, (long long)max_size, d_sel,
+					                                                         reinterpret_cast<double *>(d_sel + ((ng + 2) & ~i64(1))));
+				QTB_CUDA(cudaGetLastError());
+				ctx.counters[0] += truncate ? 2 : 1;
+				if (truncate)
+				{
+					sel_host.assign(ng + 1, 0);
+					QTB_CUDA(cudaMemcpyAsync(sel_host.data(), d_sel, (ng + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+				}
+				if (debug_census)
+					QTB_CUDA(cudaMemcpyAsync(sigma.data(), d_sigma, sig_total * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+				ctx.counters[5] += (ng + 1) * (i64)sizeof(int);
+			}
+			else
+				QTB_CUDA(cudaMemcpyAsync(sigma.data(), d_sigma, sig_total * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
 			if (eigh_mode)
 			{
 				eigh_shift.assign(ng, 0.0);
@@ -2162,10 +2381,12 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			QTB_CUDA(cudaStreamSynchronize(ctx.stream));
 			if (d_shift)
 				ctx_free(ctx, d_shift);
-			ctx.counters[5] += sig_total * (i64)sizeof(double);
+			if (!dev_select)
+				ctx.counters[5] += sig_total * (i64)sizeof(double);
 		}
 	}
-	if (std::getenv("QTB_SVD_DEBUG") && std::atoi(std::getenv("QTB_SVD_DEBUG")) >= 2 && sig_total > 0)
+	mark(3);
+	if (debug_census && sig_total > 0)
 	{ // spectrum census of this call
 		double smax = 0;
 		for (double v : sigma)
@@ -2185,7 +2406,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	}
 	// per group: permutation sorting sigma descending (LAPACK's order); eigenvalues e = sigma - shift ascending
 	std::vector<double> dval(sigma); // what goes into D, per column of the workspace
-	for (i64 g = 0; g < ng; ++g)
+	for (i64 g = 0; g < ng && !dev_select; ++g)
 	{
 		int *p = perm.data() + sig_off[g];
 		std::iota(p, p + dg[g].n, 0);
@@ -2256,6 +2477,25 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			}
 		}
 	}
+	else if (truncate && sig_total > 0 && dev_select)
+	{ // kept counts from svd_select_kernel; the block bookkeeping of truncate_impl stays on the host
+		QTB_REQUIRE(sel_host[0] >= 0, QTB_ERR_OUT_OF_RANGE, "truncate: index -1 is out of bounds (min_size = 0 with a full discard)");
+		std::vector<i64> u_last(ub.size()), v_last(vb.size());
+		for (size_t i = 0; i < ub.size(); ++i)
+			u_last[i] = ub[i].group;
+		for (size_t i = 0; i < vb.size(); ++i)
+			v_last[i] = vb[i].group;
+		for (i64 g = ng - 1; g >= 0; --g)
+		{
+			kept[g] = sel_host[1 + g];
+			if (kept[g] == 0)
+			{
+				d_alive[g] = 0;
+				u_alive = remove_unit_blocks(u_last, g, u_alive);
+				v_alive = remove_unit_blocks(v_last, g, v_alive);
+			}
+		}
+	}
 	else if (truncate && sig_total > 0)
 	{
 		std::vector<double> vd;
@@ -2307,7 +2547,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 		if (d_alive[g])
 		{
 			D->index.push_back(g);
-			for (i64 j = 0; j < kept[g]; ++j)
+			for (i64 j = 0; j < kept[g] && !dev_select; ++j)
 				dvals.push_back(dval[sig_off[g] + perm[sig_off[g] + j]]);
 		}
 	D->nblocks = (i64)D->index.size();
@@ -2317,7 +2557,24 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	{
 		const i64 total = D->layout_packed();
 		D->arena = std::make_shared<Arena>(&ctx, total);
-		if (total > 0)
+		if (total > 0 && dev_select)
+		{ // the kept values of every live sector, straight from the device-sorted list
+			std::vector<GatherDesc> gd;
+			for (i64 b = 0; b < D->nblocks; ++b)
+			{
+				GatherDesc gdesc{};
+				gdesc.src_off = sig_off[D->index[b]];
+				gdesc.dst_off = D->offs[b];
+				gdesc.numel = kept[D->index[b]];
+				gdesc.rank = 1;
+				gdesc.dims[0] = gdesc.numel;
+				gdesc.strides[0] = 1;
+				if (gdesc.numel > 0)
+					gd.push_back(gdesc);
+			}
+			launch_gather(ctx, gd, d_sorted, D->arena->ptr);
+		}
+		else if (total > 0)
 		{
 			auto tmp = ctx_upload(ctx, dvals.data(), dvals.size() * sizeof(double));
 			QTB_CUDA(cudaMemcpyAsync(D->arena->ptr, tmp, dvals.size() * sizeof(double), cudaMemcpyDeviceToDevice, ctx.stream));
@@ -2419,13 +2676,14 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 		if (!sd.empty())
 		{
 			auto d_sd = ctx_upload(ctx, sd.data(), sd.size() * sizeof(ScatterDesc));
-			auto d_perm = ctx_upload(ctx, perm.data(), perm.size() * sizeof(int));
+			auto d_perm = dev_select ? (void *)d_perm_dev : ctx_upload(ctx, perm.data(), perm.size() * sizeof(int));
 			dim3 grid(8, (unsigned)std::min<size_t>(sd.size(), 4096));
 			svd_scatter_kernel<<<grid, 256, 0, ctx.stream>>>((const ScatterDesc *)d_sd, (int)sd.size(), X, (const int *)d_perm,
 			                                                d_sigma, T->arena->ptr);
 			QTB_CUDA(cudaGetLastError());
 			ctx_free(ctx, d_sd);
-			ctx_free(ctx, d_perm);
+			if (!dev_select)
+				ctx_free(ctx, d_perm);
 			ctx.counters[0] += 1;
 		}
 		if (sharded)
@@ -2436,6 +2694,12 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	build(U, 0, split, false, a.st.sel, ub, u_alive, true);
 	if (!eigh_mode)
 		build(V, split, r, true, neutral, vb, v_alive, false);
+	if (d_perm_dev)
+	{
+		ctx_free(ctx, d_perm_dev);
+		ctx_free(ctx, d_sorted);
+		ctx_free(ctx, d_sel);
+	}
 	if (ng > 0)
 	{
 		ctx_free(ctx, X);
@@ -2443,6 +2707,10 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 		ctx_free(ctx, d_sigoff);
 		ctx_free(ctx, d_sigma);
 	}
+	mark(4);
+	if (debug_census)
+		std::fprintf(stderr, "[qtb svd] phases ms: densify %.2f | qr %.2f | jacobi %.2f | norms+apply-Q+select %.2f | truncate+scatter %.2f\n",
+		             phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3], phase_ms[4]);
 }
 
 void block_svd(Ctx &ctx, const Tensor &a, i64 split, bool truncate, double tol, i64 min_size, i64 max_size, double pw,
