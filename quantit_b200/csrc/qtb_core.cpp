@@ -1258,8 +1258,14 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 					c = 200.0 + (double)o.M / 256.0 * (double)ksum * (4.0 + o.N);
 				else
 				{
-					// the busiest consumer warp of a tile always computes its whole warp tile (unpredicated path)
-					c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * (wm / 8) * (wn / 8));
+					if (plan->tile_cfg == 0)
+					{ // 64 x 64: the four warps share the valid 8x8 atoms of the tile (gemm_warp_grid)
+						int gm, gn, am, an;
+						gemm_warp_grid(std::min(8, (int)(o.M - m0 + 7) / 8), std::min(8, (int)(o.N - n0 + 7) / 8), gm, gn, am, an);
+						c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * am * an);
+					}
+					else // 128 x 128: the busiest consumer warp always computes its whole warp tile (unpredicated path)
+						c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * (wm / 8) * (wn / 8));
 				}
 				{
 					const GemmPair &p0 = plan->pairs[o.pair_begin];

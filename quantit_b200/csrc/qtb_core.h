@@ -152,6 +152,47 @@ constexpr i64 kBlockAlign = 1; // packed blocks sit back to back: the arena imag
 std::vector<i64> sort_blocks(i64 rank, std::vector<i64> &index);
 
 // ---- contraction plan ----------------------------------------------------------------------------------------------
+// 64 x 64 configuration: how the four consumer warps share the 8 x 8 grid of 8x8 MMA atoms of a tile that holds only
+// mv x nv valid atoms (block edges). The warps form a gm x gn grid, (2,2), (1,4) or (4,1), each owning am x an atoms
+// (am, an <= 4); the shape with the fewest atoms on the busiest warp wins. A full tile is (2,2) with 4 x 4 atoms each.
+// Used by the kernel (qtb_gemm.cu) and by the planner's cost model, which must agree.
+#if defined(__CUDACC__)
+#define QTB_HD __host__ __device__
+#else
+#define QTB_HD
+#endif
+QTB_HD inline void gemm_warp_grid(int mv, int nv, int &gm, int &gn, int &am, int &an)
+{
+	gm = 2;
+	gn = 2;
+	am = (mv + 1) >> 1;
+	an = (nv + 1) >> 1;
+	int best = am * an;
+	if (mv <= 4)
+	{ // one row of warps
+		const int a = mv, b = (nv + 3) >> 2;
+		if (a * b < best)
+		{
+			best = a * b;
+			gm = 1;
+			gn = 4;
+			am = a;
+			an = b;
+		}
+	}
+	if (nv <= 4)
+	{ // one column of warps
+		const int a = (mv + 3) >> 2, b = nv;
+		if (a * b < best)
+		{
+			gm = 4;
+			gn = 1;
+			am = a;
+			an = b;
+		}
+	}
+}
+
 struct GemmTile
 { // one work item of the grouped GEMM: a tile of one output block, self-contained (the kernels fetch ONE descriptor per
   // item, no dependent second fetch of the block's record)

@@ -87,6 +87,7 @@ struct GemmCfg
 {
 	static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
 	static constexpr bool REALLOC = REALLOC_;
+	static constexpr bool kEdge = (BM_ == 64 && BN_ == 64 && WM_ == 32 && WN_ == 32); // per-tile warp grid + atom-count variants
 	static constexpr int kWarpsM = BM / WM;
 	static constexpr int kWarpsN = BN / WN;
 	static constexpr int kConsWarps = kWarpsM * kWarpsN;
@@ -172,6 +173,99 @@ __device__ __forceinline__ void load_tile(unsigned smem_dst, const double *__res
 	}
 }
 
+// Affine operands (element (r,k) at base + r*rs + k*ks, one of the strides 1 — every block on the tensordot / DMRG hot
+// path): the producer's fast path. The first version recomputed every element address from (r, k) in every K chunk
+// (IMAD.WIDE + LEA pairs, row clamps, k clamps: ~300 instructions per thread and chunk on configs[1], where most tiles
+// touch a block edge) and the producer warpgroup, not the tensor pipe, set the chunk rate (ncu source view,
+// profiles/r2: producers 68 % busy issuing, consumers 22 % waiting on the full barrier; shrinking the DMMA work by a
+// quarter did not move the kernel time). Here a thread's PER elements of a chunk are an arithmetic progression
+// ptr + i*step (i-th row of its k column, or i-th k of its row), set up once per (tile, pair); a chunk costs one
+// 64-bit add + one LDGSTS per element, elements past the block edge or the K tail are zero-filled (src-size 0: the
+// address is never dereferenced) and are exactly the progression's tail i >= n_ok.
+struct AffineRun
+{
+	const double *ptr; // element 0 of the current chunk
+	long long step;    // elements between consecutive i
+	long long kadv;    // elements per K chunk
+	int nfix;          // kc: valid rows of this thread (0..PER); else: PER if the thread's row is inside the block, 0 if not
+	int koff;          // kc: the thread's k inside a chunk; else: its first k
+	unsigned dst;      // byte offset of element 0 inside the operand's stage slot
+};
+
+template <class Cfg, int R>
+__device__ __forceinline__ AffineRun affine_setup(int kc, const double *__restrict__ base, int rs, int ks, int r0,
+                                                  int Rmax, int pt)
+{
+	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads, PER = R * BK / NT;
+	AffineRun a;
+	a.kadv = (long long)BK * ks;
+	if (kc)
+	{
+		const int k = pt % BK, rbase = pt / BK;
+		a.ptr = base + (long long)(r0 + rbase) * rs + (long long)k * ks;
+		a.step = (long long)(NT / BK) * rs;
+		const int left = (Rmax - r0 - rbase + (NT / BK) - 1) / (NT / BK);
+		a.nfix = left < 0 ? 0 : (left > PER ? PER : left);
+		a.koff = k;
+		a.dst = (unsigned)(rbase * (BK + PAD) + k) * 8u;
+	}
+	else
+	{
+		const int r = pt % R, kbase = pt / R;
+		a.ptr = base + (long long)(r0 + r) * rs + (long long)kbase * ks;
+		a.step = (long long)(NT / R) * ks;
+		a.nfix = (r0 + r < Rmax) ? PER : 0;
+		a.koff = kbase;
+		a.dst = (unsigned)(kbase * (R + PAD) + r) * 8u;
+	}
+	return a;
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void affine_issue(int kc, AffineRun &a, unsigned slot, int k0, int K)
+{
+	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads, PER = R * BK / NT;
+	const double *src = a.ptr;
+	a.ptr += a.kadv;
+	const unsigned dst = slot + a.dst;
+	if (kc)
+	{
+		constexpr unsigned DS = (NT / BK) * (BK + PAD) * 8;
+		const int n_ok = (k0 + a.koff < K) ? a.nfix : 0;
+		if (n_ok == PER)
+		{
+#pragma unroll
+			for (int i = 0; i < PER; ++i, src += a.step)
+				cp_async8_full(dst + i * DS, src);
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < PER; ++i, src += a.step)
+				cp_async8(dst + i * DS, src, i < n_ok);
+		}
+	}
+	else
+	{
+		constexpr unsigned DS = (NT / R) * (R + PAD) * 8;
+		int left = (K - k0 - a.koff + (NT / R) - 1) / (NT / R);
+		left = left < 0 ? 0 : left;
+		const int n_ok = left < a.nfix ? left : a.nfix;
+		if (n_ok == PER)
+		{
+#pragma unroll
+			for (int i = 0; i < PER; ++i, src += a.step)
+				cp_async8_full(dst + i * DS, src);
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < PER; ++i, src += a.step)
+				cp_async8(dst + i * DS, src, i < n_ok);
+		}
+	}
+}
+
 template <class Cfg, int R>
 __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned smem_dst, const double *__restrict__ base,
                                              const int32_t *__restrict__ rtab, const int32_t *__restrict__ ktab, int rs,
@@ -210,12 +304,12 @@ __device__ __noinline__ void load_operand(int kcontig, bool affine, unsigned sme
 // latency (ncu source view of configs[1], profiles/r2: the short-scoreboard samples sit on the DMMA after every LDS,
 // tensor pipe 44 % active). Here every offset is an immediate and the fragments of k-step kk + 1 are requested before
 // the 16 (32) DMMAs of k-step kk issue.
-template <class Cfg, bool AKC, bool BNC>
+// MI x NI: the 8x8 atoms this warp computes (the whole warp tile, or fewer on block edges of the 64 x 64 configuration).
+template <class Cfg, bool AKC, bool BNC, int MI, int NI>
 __device__ __forceinline__ void mma_chunk(double (&acc)[Cfg::WM / 8][Cfg::WN / 8][2], const double *__restrict__ As,
                                           const double *__restrict__ Bs, int wm0, int wn0, int g, int q, int shA, int shB)
 {
 	constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, PAD = Cfg::kPad;
-	constexpr int MI = Cfg::WM / 8, NI = Cfg::WN / 8;
 	constexpr int sa_m = AKC ? (BK + PAD) : 1, sa_k = AKC ? 1 : (BM + PAD);
 	constexpr int sb_k = BNC ? (BN + PAD) : 1, sb_n = BNC ? 1 : (BK + PAD);
 	const double *Ap = As + (wm0 + g) * sa_m + q * sa_k + shA;
@@ -245,6 +339,65 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[Cfg::WM / 8][Cfg::WN / 8
 #pragma unroll
 			for (int j = 0; j < NI; ++j)
 				dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+	}
+}
+
+// All K chunks of one tile for one consumer warp that owns MIV x NJV atoms at (wm0, wn0); MIV == 0: the warp has no
+// valid atom in this tile and only keeps the ring moving.
+template <class Cfg, int MIV, int NJV>
+__device__ __forceinline__ void consume_tile(double (&acc)[Cfg::WM / 8][Cfg::WN / 8][2], const GemmTile &ob,
+                                             const GemmPair *__restrict__ pairs, int bulk_mask, const double *smem,
+                                             unsigned full0, unsigned empty0, int &stage, unsigned &phase, int wm0,
+                                             int wn0, int g, int q, int lane)
+{
+	constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES;
+	int K = ob.K0, lay = ob.flags0, shf = ob.shf0 & bulk_mask;
+	for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+	{
+		int K_next = 0, lay_next = 0, shf_next = 0;
+		if (p + 1 < ob.pair_end)
+		{
+			K_next = pairs[p + 1].K;
+			lay_next = pairs[p + 1].a_kcontig | (pairs[p + 1].b_ncontig << 1);
+			shf_next = pairs[p + 1].shf & bulk_mask;
+		}
+		const int a_kc = lay & 1, b_nc = lay >> 1;
+		// one-element shifts of the bulk-staged runs (see the producer): the run index is the fragment row g (A rows /
+		// B columns when k is the unit-stride direction) or the fragment k index q; every other term of the run's
+		// source address (tile origins, chunk origins, warp and MMA offsets) is even
+		const int shA = (shf & 1) ? (((shf >> 2) & 1) + ((a_kc ? g : q) & 1) * ((shf >> 3) & 1)) & 1 : 0;
+		const int shB = (shf & 2) ? (((shf >> 4) & 1) + ((b_nc ? q : g) & 1) * ((shf >> 5) & 1)) & 1 : 0;
+		const int nchunk = (K + BK - 1) / BK;
+		for (int ch = 0; ch < nchunk; ++ch)
+		{
+			mbar_wait(full0 + 8 * stage, phase);
+			if constexpr (MIV > 0)
+			{
+				const double *As = smem + stage * Cfg::kStage;
+				const double *Bs = As + Cfg::kASize;
+				// rows / columns past the block edge inside an atom were clamped by the producer (finite data, never
+				// stored) and the K tail is zero-filled: no predicate inside the loop
+				if (lay == 0)
+					mma_chunk<Cfg, false, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+				else if (lay == 1)
+					mma_chunk<Cfg, true, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+				else if (lay == 2)
+					mma_chunk<Cfg, false, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+				else
+					mma_chunk<Cfg, true, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(empty0 + 8 * stage);
+			if (++stage == STAGES)
+			{
+				stage = 0;
+				phase ^= 1;
+			}
+		}
+		K = K_next;
+		lay = lay_next;
+		shf = shf_next;
 	}
 }
 
@@ -312,6 +465,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				const bool a_aff = pr.a_rs >= 0, b_aff = pr.b_cs >= 0;
 				const int shf = pr.shf & bulk_mask;
 				const int nchunk = (pr.K + BK - 1) / BK;
+				// affine operands outside the bulk-staged layout: the pointer-progression fast path
+				const bool a_fast = a_aff && !(shf & 1), b_fast = b_aff && !(shf & 2);
+				AffineRun fa, fb;
+				if (a_fast)
+					fa = affine_setup<Cfg, BM>(pr.a_kcontig, Ab, pr.a_rs, pr.a_ks, m0, M, pt);
+				if (b_fast)
+					fb = affine_setup<Cfg, BN>(!pr.b_ncontig, Bb, pr.b_cs, pr.b_ks, n0, N, pt);
 				for (int ch = 0; ch < nchunk; ++ch)
 				{
 					mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -389,10 +549,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 						if (b_bytes)
 							bulk_g2s(b_dst, b_src, b_bytes, fullb);
 					}
-					if (!a_bulk)
+					if (a_fast)
+						affine_issue<Cfg, BM>(pr.a_kcontig, fa, As, k0, pr.K);
+					else if (!a_bulk)
 						load_operand<Cfg, BM>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt,
 						                      (shf & 1) ? (shf >> 2) & 1 : 0, (shf & 1) ? (shf >> 3) & 1 : 0);
-					if (!b_bulk)
+					if (b_fast)
+						affine_issue<Cfg, BN>(!pr.b_ncontig, fb, Bs, k0, pr.K);
+					else if (!b_bulk)
 						load_operand<Cfg, BN>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt,
 						                      (shf & 2) ? (shf >> 4) & 1 : 0, (shf & 2) ? (shf >> 5) & 1 : 0);
 					mbar_arrive_cp_async(full0 + 8 * stage);
@@ -416,8 +580,6 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		if constexpr (Cfg::REALLOC)
 			asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n");
 		const int cw = warp - 4;
-		const int wm0 = (cw / Cfg::kWarpsN) * WM;
-		const int wn0 = (cw % Cfg::kWarpsN) * WN;
 		const int g = lane >> 2; // fragment row (A) / column (B) inside an 8x8x4 MMA
 		const int q = lane & 3;  // fragment k index
 		constexpr int MI = WM / 8;
@@ -435,11 +597,30 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 			const GemmTile ob = tile;
 			tile = next;
 			const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
-			// number of 8-row / 8-column MMA groups of this warp that intersect the block
-			int mi_valid = (M - m0 - wm0 + 7) / 8;
-			mi_valid = mi_valid < 0 ? 0 : (mi_valid > MI ? MI : mi_valid);
-			int nj_valid = (N - n0 - wn0 + 7) / 8;
-			nj_valid = nj_valid < 0 ? 0 : (nj_valid > NI ? NI : nj_valid);
+			// atoms (8 rows x 8 columns) of this warp that intersect the block. 128 x 128: the static 2 x 4 warp grid, a warp
+			// that intersects the block computes its whole tile. 64 x 64: the four warps share the valid atoms of the tile
+			// (gemm_warp_grid) and run a loop compiled for exactly their atom count: on configs[1] (blocks of 1..136 rows)
+			// the static grid left 22 % of the consumer samples on warps with no valid atom and 1.49x padded DMMA work.
+			int wm0 = (cw / Cfg::kWarpsN) * WM, wn0 = (cw % Cfg::kWarpsN) * WN;
+			int mi_valid, nj_valid;
+			if constexpr (Cfg::kEdge)
+			{
+				const int mv = min(BM / 8, (M - m0 + 7) >> 3), nv = min(BN / 8, (N - n0 + 7) >> 3);
+				int gm, gn, am, an;
+				gemm_warp_grid(mv, nv, gm, gn, am, an);
+				const int wi = cw / gn, wj = cw - wi * gn;
+				wm0 = wi * am * 8;
+				wn0 = wj * an * 8;
+				mi_valid = max(0, min(am, mv - wi * am));
+				nj_valid = max(0, min(an, nv - wj * an));
+			}
+			else
+			{
+				mi_valid = (M - m0 - wm0 + 7) / 8;
+				mi_valid = mi_valid < 0 ? 0 : (mi_valid > MI ? MI : mi_valid);
+				nj_valid = (N - n0 - wn0 + 7) / 8;
+				nj_valid = nj_valid < 0 ? 0 : (nj_valid > NI ? NI : nj_valid);
+			}
 			const bool any = (mi_valid > 0) && (nj_valid > 0);
 
 			double acc[MI][NI][2];
@@ -449,57 +630,36 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				for (int j = 0; j < NI; ++j)
 					acc[i][j][0] = acc[i][j][1] = 0.0;
 
-			int K = ob.K0, lay = ob.flags0, shf = ob.shf0 & bulk_mask;
-			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+#define QTB_CONSUME(MIV, NJV) \
+	consume_tile<Cfg, MIV, NJV>(acc, ob, pairs, bulk_mask, smem, full0, empty0, stage, phase, wm0, wn0, g, q, lane)
+			if (!any)
+				QTB_CONSUME(0, 0);
+			else if constexpr (Cfg::kEdge)
 			{
-				int K_next = 0, lay_next = 0, shf_next = 0;
-				if (p + 1 < ob.pair_end)
+				static_assert(!Cfg::kEdge || (MI == 4 && NI == 4), "edge variants are written for 4 x 4 atoms per warp");
+				switch (mi_valid * 4 + nj_valid - 5)
 				{
-					K_next = pairs[p + 1].K;
-					lay_next = pairs[p + 1].a_kcontig | (pairs[p + 1].b_ncontig << 1);
-					shf_next = pairs[p + 1].shf & bulk_mask;
+				case 0: QTB_CONSUME(1, 1); break;
+				case 1: QTB_CONSUME(1, 2); break;
+				case 2: QTB_CONSUME(1, 3); break;
+				case 3: QTB_CONSUME(1, 4); break;
+				case 4: QTB_CONSUME(2, 1); break;
+				case 5: QTB_CONSUME(2, 2); break;
+				case 6: QTB_CONSUME(2, 3); break;
+				case 7: QTB_CONSUME(2, 4); break;
+				case 8: QTB_CONSUME(3, 1); break;
+				case 9: QTB_CONSUME(3, 2); break;
+				case 10: QTB_CONSUME(3, 3); break;
+				case 11: QTB_CONSUME(3, 4); break;
+				case 12: QTB_CONSUME(4, 1); break;
+				case 13: QTB_CONSUME(4, 2); break;
+				case 14: QTB_CONSUME(4, 3); break;
+				default: QTB_CONSUME(4, 4); break;
 				}
-				const int a_kc = lay & 1, b_nc = lay >> 1;
-				// one-element shifts of the bulk-staged runs (see the producer): the run index is the fragment row g (A rows /
-				// B columns when k is the unit-stride direction) or the fragment k index q; every other term of the run's
-				// source address (tile origins, chunk origins, warp and MMA offsets) is even
-				const int shA = (shf & 1) ? (((shf >> 2) & 1) + ((a_kc ? g : q) & 1) * ((shf >> 3) & 1)) & 1 : 0;
-				const int shB = (shf & 2) ? (((shf >> 4) & 1) + ((b_nc ? q : g) & 1) * ((shf >> 5) & 1)) & 1 : 0;
-				const int nchunk = (K + BK - 1) / BK;
-				for (int ch = 0; ch < nchunk; ++ch)
-				{
-					mbar_wait(full0 + 8 * stage, phase);
-					const double *As = smem + stage * Cfg::kStage;
-					const double *Bs = As + Cfg::kASize;
-					// A warp whose 32-row x 32-column (64 x 32 for the large configuration) tile intersects the block
-					// computes ALL of it, unpredicated: rows / columns past the block edge were clamped by the producer
-					// (finite data, never stored) and the K tail is zero-filled. The first version skipped invalid 8x8
-					// atoms with per-atom predicates: 6.4 instructions per DMMA on configs[1] (ncu source view, 30 % of the
-					// consumer samples on integer / branch instructions) to save 1.49x -> 1.14x of padded DMMA work.
-					if (any)
-					{
-						if (lay == 0)
-							mma_chunk<Cfg, false, false>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-						else if (lay == 1)
-							mma_chunk<Cfg, true, false>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-						else if (lay == 2)
-							mma_chunk<Cfg, false, true>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-						else
-							mma_chunk<Cfg, true, true>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-					}
-					__syncwarp();
-					if (lane == 0)
-						mbar_arrive(empty0 + 8 * stage);
-					if (++stage == STAGES)
-					{
-						stage = 0;
-						phase ^= 1;
-					}
-				}
-				K = K_next;
-				lay = lay_next;
-				shf = shf_next;
 			}
+			else
+				QTB_CONSUME(MI, NI);
+#undef QTB_CONSUME
 
 			// epilogue: the output block is a fresh packed row-major [M,N] matrix
 			if (any)
@@ -509,11 +669,13 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				for (int i = 0; i < MI; ++i)
 				{
 					const int m = m0 + wm0 + i * 8 + g;
-					if (m < M)
+					if (m < M && i < mi_valid)
 					{
 #pragma unroll
 						for (int j = 0; j < NI; ++j)
 						{
+							if (j >= nj_valid)
+								continue; // atoms beyond this warp's share belong to another warp (64 x 64 configuration)
 							const int n = n0 + wn0 + j * 8 + 2 * q;
 							double *dst = Cb + (size_t)m * N + n;
 							if (Cin != nullptr)
