@@ -1,0 +1,12 @@
+#!/bin/bash
+# round-2 session 37: distinct LDGSTS address registers: tests + T1 / T2
+mkdir -p gpurun_out/r2
+( timeout 900 python -m pytest tests -m gpu -x -q -k "tensordot or gemm or contract or config or heff or capi" 2>&1 | tail -3 ) > gpurun_out/r2/s37.txt
+for w in T1 T2; do
+  timeout 300 python bench.py --steps 100 --warmup 5 --no-extra --workload $w 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$w value', round(d['value'],3), d['unit'], 'ms', round(d['ms_per_step'],5), 'frac', round(d['roofline']['frac'],4))
+" >> gpurun_out/r2/s37.txt
+done
+cat gpurun_out/r2/s37.txt

@@ -1277,7 +1277,9 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	}
 	// Bulk (UBLKCP) staging pays with 128 x 128 tiles (runs of 1 KB); with 64 x 64 tiles the runs are 128-512 bytes and the
 	// per-request cost of the TMA unit makes it slower than LDGSTS (configs[1]: 81 us against 75 us, profiles/r2/s17.txt)
-	if (plan->tile_cfg != 1)
+	// With 64 x 64 tiles the same shifted layout is filled by 16-byte LDGSTS instead (QTB_VEC16=0: plain 8-byte copies).
+	static const bool vec16_on = !(std::getenv("QTB_VEC16") && std::atoi(std::getenv("QTB_VEC16")) == 0);
+	if (plan->tile_cfg == 2 || (plan->tile_cfg == 0 && !vec16_on))
 	{
 		for (auto &pr : plan->pairs)
 			pr.shf = 0;

@@ -22,6 +22,7 @@
 //    heaviest first); work items are self-contained records fetched ahead of use. At ragged block edges a warp tile that
 //    intersects the block is computed whole (clamped rows, zero-filled K tail), a warp tile outside it is skipped.
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstdint>
@@ -87,6 +88,7 @@ struct GemmCfg
 {
 	static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
 	static constexpr bool REALLOC = REALLOC_;
+	static constexpr bool kVec16 = (BM_ == 64 && BN_ == 64); // shifted-layout operands: 16-byte LDGSTS (else the bulk path)
 	static constexpr bool kEdge = (BM_ == 64 && BN_ == 64 && WM_ == 32 && WN_ == 32); // per-tile warp grid + atom-count variants
 	static constexpr int kWarpsM = BM / WM;
 	static constexpr int kWarpsN = BN / WN;
@@ -98,7 +100,10 @@ struct GemmCfg
 	static constexpr int kASize = (BM * (BK + kPad) > BK * (BM + kPad)) ? BM * (BK + kPad) : BK * (BM + kPad);
 	static constexpr int kBSize = (BN * (BK + kPad) > BK * (BN + kPad)) ? BN * (BK + kPad) : BK * (BN + kPad);
 	static constexpr int kStage = kASize + kBSize;
-	static constexpr size_t kSmemBytes = size_t(STAGES) * kStage * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+	// + descriptor ring: kTileRing work-item records and two pair records, staged by the producer warpgroup
+	static constexpr int kTileRing = 16;
+	static constexpr size_t kDescOff = (size_t(STAGES) * kStage * sizeof(double) + 2 * STAGES * sizeof(uint64_t) + 15) & ~size_t(15);
+	static constexpr size_t kSmemBytes = kDescOff + kTileRing * 48 + 2 * 64;
 	static constexpr int kAPerThread = BM * BK / kProdThreads;
 	static constexpr int kBPerThread = BN * BK / kProdThreads;
 	static_assert(BM * BK % kProdThreads == 0 && BN * BK % kProdThreads == 0, "tile/threads mismatch");
@@ -225,44 +230,178 @@ template <class Cfg, int R>
 __device__ __forceinline__ void affine_issue(int kc, AffineRun &a, unsigned slot, int k0, int K)
 {
 	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads, PER = R * BK / NT;
-	const double *src = a.ptr;
+	// every address in its own register pair BEFORE the first copy issues: an LDGSTS holds its address registers until
+	// the load/store unit takes it, and a single running pointer made every copy wait for the previous one to leave the
+	// queue (ncu source view: long-scoreboard samples on each pointer increment)
+	const double *src[PER];
+#pragma unroll
+	for (int i = 0; i < PER; ++i)
+	{
+		src[i] = a.ptr + i * a.step;
+		asm volatile("" : "+l"(src[i])); // opaque: keeps ptxas from rematerialising the address into a shared register pair
+	}
 	a.ptr += a.kadv;
 	const unsigned dst = slot + a.dst;
+	int n_ok;
+	if (kc)
+		n_ok = (k0 + a.koff < K) ? a.nfix : 0;
+	else
+	{
+		int left = (K - k0 - a.koff + (NT / R) - 1) / (NT / R);
+		left = left < 0 ? 0 : left;
+		n_ok = left < a.nfix ? left : a.nfix;
+	}
 	if (kc)
 	{
 		constexpr unsigned DS = (NT / BK) * (BK + PAD) * 8;
-		const int n_ok = (k0 + a.koff < K) ? a.nfix : 0;
 		if (n_ok == PER)
 		{
 #pragma unroll
-			for (int i = 0; i < PER; ++i, src += a.step)
-				cp_async8_full(dst + i * DS, src);
+			for (int i = 0; i < PER; ++i)
+				cp_async8_full(dst + i * DS, src[i]);
 		}
 		else
 		{
 #pragma unroll
-			for (int i = 0; i < PER; ++i, src += a.step)
-				cp_async8(dst + i * DS, src, i < n_ok);
+			for (int i = 0; i < PER; ++i)
+				cp_async8(dst + i * DS, src[i], i < n_ok);
 		}
 	}
 	else
 	{
 		constexpr unsigned DS = (NT / R) * (R + PAD) * 8;
-		int left = (K - k0 - a.koff + (NT / R) - 1) / (NT / R);
-		left = left < 0 ? 0 : left;
-		const int n_ok = left < a.nfix ? left : a.nfix;
 		if (n_ok == PER)
 		{
 #pragma unroll
-			for (int i = 0; i < PER; ++i, src += a.step)
-				cp_async8_full(dst + i * DS, src);
+			for (int i = 0; i < PER; ++i)
+				cp_async8_full(dst + i * DS, src[i]);
 		}
 		else
 		{
 #pragma unroll
-			for (int i = 0; i < PER; ++i, src += a.step)
-				cp_async8(dst + i * DS, src, i < n_ok);
+			for (int i = 0; i < PER; ++i)
+				cp_async8(dst + i * DS, src[i], i < n_ok);
 		}
+	}
+}
+
+// 16-byte variant of the affine fast path for operands whose unit-stride runs are staged in the shifted layout
+// (GemmPair::shf, see the bulk path): the 8-byte LDGSTS is what bounds the producer on configs[1] (64 warp-level copies
+// of 256 bytes per chunk; the load/store unit takes ~2000 cycles for them, more than the consumers need for the chunk's
+// DMMAs), a 16-byte copy moves twice as much per instruction. A run (a row of BK elements when k is the unit-stride
+// direction, else the tile's rows at one k) that starts on an odd element is fetched from one element earlier and
+// lands one element late in its slot, exactly as in the bulk path, so source and destination are both 16-byte
+// aligned; the consumers undo the shift. Pieces past the block edge / the K tail are zero-filled through src-size.
+__device__ __forceinline__ void cp_async16(unsigned smem, const void *gmem, int bytes)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async16_full(unsigned smem, const void *gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem));
+}
+struct VecRun
+{
+	const double *ptr; // piece j of run 0 of this thread, current chunk
+	long long step;    // elements between this thread's consecutive runs
+	long long kadv;    // elements per K chunk
+	int nfix;          // kc: valid runs (rows) of this thread; else unused
+	int run0;          // first run of this thread inside a chunk
+	int j;             // piece index inside a run
+	int sh;            // one-element shift of this thread's runs
+	int lv;            // !kc: valid elements of a run (rows of the tile inside the block)
+	unsigned dst;
+};
+
+template <class Cfg, int R>
+__device__ __forceinline__ VecRun vec_setup(int kc, const double *__restrict__ base, int rs, int ks, int r0, int Rmax,
+                                            int pt, int offpar, int strpar)
+{
+	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads;
+	VecRun a;
+	if (kc)
+	{
+		constexpr int P = BK / 2, RP = NT / P, PASS = R / RP;
+		a.j = pt % P;
+		a.run0 = pt / P;
+		a.sh = (offpar + (a.run0 & 1) * strpar) & 1;
+		a.ptr = base + (long long)(r0 + a.run0) * rs + 2 * a.j - a.sh;
+		a.step = (long long)RP * rs;
+		a.kadv = BK;
+		const int left = (Rmax - r0 - a.run0 + RP - 1) / RP;
+		a.nfix = left < 0 ? 0 : (left > PASS ? PASS : left);
+		a.lv = 0;
+		a.dst = (unsigned)(a.run0 * (BK + PAD) + 2 * a.j) * 8u;
+	}
+	else
+	{
+		constexpr int P = R / 2, RP = NT / P;
+		a.j = pt % P;
+		a.run0 = pt / P;
+		a.sh = (offpar + (a.run0 & 1) * strpar) & 1;
+		a.ptr = base + (long long)a.run0 * ks + r0 + 2 * a.j - a.sh;
+		a.step = (long long)RP * ks;
+		a.kadv = (long long)BK * ks;
+		a.nfix = 0;
+		a.lv = Rmax - r0 < R ? Rmax - r0 : R;
+		a.dst = (unsigned)(a.run0 * (R + PAD) + 2 * a.j) * 8u;
+	}
+	return a;
+}
+
+template <class Cfg, int R>
+__device__ __forceinline__ void vec_issue(int kc, VecRun &a, unsigned slot, int k0, int K)
+{
+	constexpr int BK = Cfg::BK, PAD = Cfg::kPad, NT = Cfg::kProdThreads;
+	constexpr int PASS = R * BK / 2 / NT; // 16-byte pieces per thread and chunk
+	const double *src[PASS];
+#pragma unroll
+	for (int i = 0; i < PASS; ++i)
+	{
+		src[i] = a.ptr + i * a.step;
+		asm volatile("" : "+l"(src[i]));
+	}
+	a.ptr += a.kadv;
+	const unsigned dst = slot + a.dst;
+	int n_ok, lv, P;
+	unsigned DS;
+	if (kc)
+	{
+		P = BK / 2;
+		DS = (NT / (BK / 2)) * (BK + PAD) * 8;
+		n_ok = a.nfix;
+		lv = K - k0 < BK ? K - k0 : BK;
+	}
+	else
+	{
+		P = R / 2;
+		DS = (NT / (R / 2)) * (R + PAD) * 8;
+		int left = (K - k0 - a.run0 + (NT / (R / 2)) - 1) / (NT / (R / 2));
+		left = left < 0 ? 0 : left;
+		n_ok = left < PASS ? left : PASS;
+		lv = a.lv;
+	}
+	int e = lv + a.sh - 2 * a.j; // elements of this piece inside the run: >= 2 whole piece, 1 half, <= 0 none
+	const int sz = e >= 2 ? 16 : (e == 1 ? 8 : 0);
+	if (n_ok == PASS && sz == 16)
+	{
+#pragma unroll
+		for (int i = 0; i < PASS; ++i)
+			cp_async16_full(dst + i * DS, src[i]);
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < PASS; ++i)
+			cp_async16(dst + i * DS, src[i], i < n_ok ? sz : 0);
+	}
+	if (a.sh && a.j == P - 1)
+	{ // the shifted run spills into one more piece (its last element)
+		e -= 2;
+		const int sz2 = e >= 2 ? 16 : (e == 1 ? 8 : 0);
+#pragma unroll
+		for (int i = 0; i < PASS; ++i)
+			cp_async16(dst + i * DS + 16, src[i] + 2, i < n_ok ? sz2 : 0);
 	}
 }
 
@@ -371,20 +510,23 @@ __device__ __forceinline__ void consume_tile(double (&acc)[Cfg::WM / 8][Cfg::WN 
 		for (int ch = 0; ch < nchunk; ++ch)
 		{
 			mbar_wait(full0 + 8 * stage, phase);
-			if constexpr (MIV > 0)
+			if (MIV > 0 && (bulk_mask & 0x100)) // bit 8 cleared: diagnostic run without the DMMAs (QTB_GEMM_DEBUG=1)
 			{
 				const double *As = smem + stage * Cfg::kStage;
 				const double *Bs = As + Cfg::kASize;
 				// rows / columns past the block edge inside an atom were clamped by the producer (finite data, never
 				// stored) and the K tail is zero-filled: no predicate inside the loop
-				if (lay == 0)
-					mma_chunk<Cfg, false, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-				else if (lay == 1)
-					mma_chunk<Cfg, true, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-				else if (lay == 2)
-					mma_chunk<Cfg, false, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
-				else
-					mma_chunk<Cfg, true, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+				if constexpr (MIV > 0)
+				{
+					if (lay == 0)
+						mma_chunk<Cfg, false, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+					else if (lay == 1)
+						mma_chunk<Cfg, true, false, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+					else if (lay == 2)
+						mma_chunk<Cfg, false, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+					else
+						mma_chunk<Cfg, true, true, MIV, NJV>(acc, As, Bs, wm0, wn0, g, q, shA, shB);
+				}
 			}
 			__syncwarp();
 			if (lane == 0)
@@ -418,6 +560,20 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 	const int warp = tid >> 5;
 	const int lane = tid & 31;
 
+	// static schedule from the planner: this CTA runs tiles [t_begin, t_end), heaviest first (LPT over modelled cycles)
+	const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
+	// Descriptor ring in shared memory. First version: every thread kept the current / next / next-but-one work item and
+	// two pair records in registers (80 registers of look-ahead); under the 128-register cap ptxas spilled them right
+	// after the loads, which turned every prefetch into a blocking load (ncu source view of the kernel skeleton,
+	// profiles/r2: 40 % of the producer samples on the STL after a descriptor LDG; the skeleton alone — no copies, no
+	// DMMAs — took 27 us of the 56). Now ONE 4-byte word per producer thread is in flight: threads 0-15 hold the next
+	// pair record, threads 32-43 the work item two tiles ahead; they are published to shared memory at the next pair /
+	// tile boundary (named barrier of the producer warpgroup) and both sides read the records from there.
+	static_assert(sizeof(GemmTile) == 48 && sizeof(GemmPair) == 64, "descriptor ring layout");
+	int32_t *s_tile_w = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(smem) + Cfg::kDescOff);
+	int32_t *s_pair_w = s_tile_w + Cfg::kTileRing * 12;
+	const GemmTile *s_tiles = reinterpret_cast<const GemmTile *>(s_tile_w);
+	const GemmPair *s_pairs = reinterpret_cast<const GemmPair *>(s_pair_w);
 	if (tid == 0)
 	{
 		for (int s = 0; s < STAGES; ++s)
@@ -426,10 +582,10 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 			mbar_init(empty0 + 8 * s, Cfg::kConsWarps);
 		}
 	}
+	if (tid < 24 && t_begin + tid / 12 < t_end)
+		s_tile_w[((t_begin + tid / 12) % Cfg::kTileRing) * 12 + tid % 12] =
+		    reinterpret_cast<const int32_t *>(tiles + t_begin + tid / 12)[tid % 12];
 	__syncthreads();
-
-	// static schedule from the planner: this CTA runs tiles [t_begin, t_end), heaviest first (LPT over modelled cycles)
-	const int t_begin = cta_begin[blockIdx.x], t_end = cta_begin[blockIdx.x + 1];
 
 	if (warp < 4)
 	{
@@ -439,23 +595,42 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		const int pt = tid; // 0..127
 		int stage = 0;
 		unsigned phase = 0;
-		// Descriptor look-ahead (ncu, configs[1]: the consumers spun 11 times per chunk on the full barrier because every
-		// tile cost the producer a tiles[] -> pairs[] -> operand chain of three dependent DRAM round trips while the ring
-		// only holds about one tile of chunks): the work item is fetched two tiles ahead and its first pair descriptor
-		// one tile ahead, so at a tile boundary the operand loads issue immediately.
-		const int t_last = t_end - 1;
-		GemmTile tile = tiles[t_begin < t_end ? t_begin : 0];
-		GemmTile next = tiles[t_begin + 1 <= t_last ? t_begin + 1 : (t_begin < t_end ? t_begin : 0)];
-		GemmPair pr0 = pairs[tile.pair_begin];
+		int32_t reg_pair = 0, reg_tile = 0; // the word of the next pair record / of work item t + 2 this thread carries
+		if (t_begin < t_end)
+		{
+			if (pt < 16)
+				reg_pair = reinterpret_cast<const int32_t *>(pairs + s_tiles[t_begin % Cfg::kTileRing].pair_begin)[pt];
+			if (pt >= 32 && pt < 44 && t_begin + 2 < t_end)
+				reg_tile = reinterpret_cast<const int32_t *>(tiles + t_begin + 2)[pt - 32];
+		}
+		int visit = 0;
 		for (int t = t_begin; t < t_end; ++t)
 		{
-			const GemmTile next2 = tiles[t + 2 <= t_last ? t + 2 : t];
-			const GemmPair pr0_next = pairs[next.pair_begin];
-			const GemmTile ob = tile;
-			const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
-			for (int p = ob.pair_begin; p < ob.pair_end; ++p)
+			GemmTile ob;
+			int p = 0;
+			for (bool first = true;; first = false)
 			{
-				const GemmPair pr = (p == ob.pair_begin) ? pr0 : pairs[p];
+				// ---- pair boundary: publish the record carried in registers, read it back, start the next fetch ----
+				if (pt < 16)
+					s_pair_w[(visit & 1) * 16 + pt] = reg_pair;
+				if (first && t > t_begin && t + 1 < t_end && pt >= 32 && pt < 44)
+					s_tile_w[((t + 1) % Cfg::kTileRing) * 12 + pt - 32] = reg_tile;
+				asm volatile("bar.sync 1, 128;\n" ::: "memory");
+				if (first)
+				{
+					ob = s_tiles[t % Cfg::kTileRing];
+					p = ob.pair_begin;
+					if (pt >= 32 && pt < 44 && t + 2 < t_end)
+						reg_tile = reinterpret_cast<const int32_t *>(tiles + t + 2)[pt - 32];
+				}
+				const GemmPair pr = s_pairs[visit & 1];
+				++visit;
+				{
+					const int np = p + 1 < ob.pair_end ? p + 1 : (t + 1 < t_end ? s_tiles[(t + 1) % Cfg::kTileRing].pair_begin : -1);
+					if (pt < 16 && np >= 0)
+						reg_pair = reinterpret_cast<const int32_t *>(pairs + np)[pt];
+				}
+				const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
 				const double *Ab = A + pr.a_off;
 				const double *Bb = B + pr.b_off;
 				const int32_t *aro = offpool + pr.a_roff;
@@ -467,11 +642,18 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				const int nchunk = (pr.K + BK - 1) / BK;
 				// affine operands outside the bulk-staged layout: the pointer-progression fast path
 				const bool a_fast = a_aff && !(shf & 1), b_fast = b_aff && !(shf & 2);
+				// 64 x 64 configuration: shifted-layout operands take 16-byte LDGSTS instead of the bulk path
+				const bool a_vec = Cfg::kVec16 && (shf & 1), b_vec = Cfg::kVec16 && (shf & 2);
 				AffineRun fa, fb;
+				VecRun va, vb;
 				if (a_fast)
 					fa = affine_setup<Cfg, BM>(pr.a_kcontig, Ab, pr.a_rs, pr.a_ks, m0, M, pt);
 				if (b_fast)
 					fb = affine_setup<Cfg, BN>(!pr.b_ncontig, Bb, pr.b_cs, pr.b_ks, n0, N, pt);
+				if (a_vec)
+					va = vec_setup<Cfg, BM>(pr.a_kcontig, Ab, pr.a_rs, pr.a_ks, m0, M, pt, (shf >> 2) & 1, (shf >> 3) & 1);
+				if (b_vec)
+					vb = vec_setup<Cfg, BN>(!pr.b_ncontig, Bb, pr.b_cs, pr.b_ks, n0, N, pt, (shf >> 4) & 1, (shf >> 5) & 1);
 				for (int ch = 0; ch < nchunk; ++ch)
 				{
 					mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -487,7 +669,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 					// (whatever the slot holds only reaches accumulators that are never stored); the K tail chunk takes the
 					// LDGSTS path below, which zero-fills and writes with the same shifts.
 					const bool kfull = k0 + BK <= pr.K;
-					const bool a_bulk = (shf & 1) && kfull, b_bulk = (shf & 2) && kfull;
+					const bool a_bulk = !Cfg::kVec16 && (shf & 1) && kfull, b_bulk = !Cfg::kVec16 && (shf & 2) && kfull;
 					unsigned tx = 0, a_bytes = 0, b_bytes = 0, a_dst = 0, b_dst = 0;
 					const double *a_src = nullptr, *b_src = nullptr;
 					if (a_bulk)
@@ -549,13 +731,21 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 						if (b_bytes)
 							bulk_g2s(b_dst, b_src, b_bytes, fullb);
 					}
-					if (a_fast)
+					if (!(bulk_mask & 0x200))
+						; // bit 9 cleared: diagnostic run without the operand copies (QTB_GEMM_DEBUG=2)
+					else if (a_fast)
 						affine_issue<Cfg, BM>(pr.a_kcontig, fa, As, k0, pr.K);
+					else if (a_vec)
+						vec_issue<Cfg, BM>(pr.a_kcontig, va, As, k0, pr.K);
 					else if (!a_bulk)
 						load_operand<Cfg, BM>(pr.a_kcontig, a_aff, As, Ab, aro, ako, pr.a_rs, pr.a_ks, m0, M, k0, pr.K, pt,
 						                      (shf & 1) ? (shf >> 2) & 1 : 0, (shf & 1) ? (shf >> 3) & 1 : 0);
-					if (b_fast)
+					if (!(bulk_mask & 0x200))
+						;
+					else if (b_fast)
 						affine_issue<Cfg, BN>(!pr.b_ncontig, fb, Bs, k0, pr.K);
+					else if (b_vec)
+						vec_issue<Cfg, BN>(!pr.b_ncontig, vb, Bs, k0, pr.K);
 					else if (!b_bulk)
 						load_operand<Cfg, BN>(!pr.b_ncontig, b_aff, Bs, Bb, bco, bko, pr.b_cs, pr.b_ks, n0, N, k0, pr.K, pt,
 						                      (shf & 2) ? (shf >> 4) & 1 : 0, (shf & 2) ? (shf >> 5) & 1 : 0);
@@ -566,10 +756,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 						phase ^= 1;
 					}
 				}
+				if (++p >= ob.pair_end)
+					break;
 			}
-			tile = next;
-			next = next2;
-			pr0 = pr0_next;
 		}
 		// drain: the async arrivals must have fired before the CTA (and its shared memory) goes away
 		asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -590,12 +779,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 		// one computes and carries the first pair's K / layout flags; further pairs are fetched one pair ahead. (ncu,
 		// configs[1], first version: 4.7 long-scoreboard stall cycles per issued instruction from the dependent
 		// tiles[] -> outs[] -> pairs[] fetches.)
-		GemmTile tile = tiles[t_begin < t_end ? t_begin : 0];
 		for (int t = t_begin; t < t_end; ++t)
 		{
-			const GemmTile next = tiles[t + 1 < t_end ? t + 1 : t];
-			const GemmTile ob = tile;
-			tile = next;
+			// the producer published this record before it issued the chunks of tile t - 1 (the full-barrier wait orders
+			// the read); the ring is deeper than the producer can run ahead (STAGES chunks)
+			const GemmTile ob = s_tiles[t % Cfg::kTileRing];
 			const int M = ob.M, N = ob.N, m0 = ob.m0, n0 = ob.n0;
 			// atoms (8 rows x 8 columns) of this warp that intersect the block. 128 x 128: the static 2 x 4 warp grid, a warp
 			// that intersects the block computes its whole tile. 64 x 64: the four warps share the valid atoms of the tile
@@ -661,8 +849,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, Cfg::MINB)
 				QTB_CONSUME(MI, NI);
 #undef QTB_CONSUME
 
-			// epilogue: the output block is a fresh packed row-major [M,N] matrix
-			if (any)
+			// epilogue: the output block is a fresh packed row-major [M,N] matrix (bit 10 cleared: diagnostic run without it)
+			if (any && (bulk_mask & 0x400))
 			{
 				double *Cb = C + ob.c_off;
 #pragma unroll
@@ -824,7 +1012,9 @@ static void launch_cfg(Ctx &ctx, int which, const Plan &plan, const double *a, c
 		QTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
 	// the bulk-staged layout's shift parities are planned on element offsets: they hold when the arena bases are 16-byte
 	// aligned (always for the engine's own arenas; adopted blocks may not be)
-	const int bulk_mask = ~0 ^ ((reinterpret_cast<uintptr_t>(a) & 15) ? 1 : 0) ^ ((reinterpret_cast<uintptr_t>(b) & 15) ? 2 : 0);
+	static const int dbg = std::getenv("QTB_GEMM_DEBUG") ? std::atoi(std::getenv("QTB_GEMM_DEBUG")) : 0; // diagnostics: wrong results
+	const int bulk_mask = ~0 ^ ((reinterpret_cast<uintptr_t>(a) & 15) ? 1 : 0) ^ ((reinterpret_cast<uintptr_t>(b) & 15) ? 2 : 0) ^
+	                      ((dbg & 7) << 8);
 	kern<<<ncta, Cfg::kThreads, Cfg::kSmemBytes, ctx.stream>>>(d_tiles, d_cta_begin, plan.d_pairs,
 	                                                            plan.d_offpool, a, b, c, bulk_mask, cin, alpha, beta);
 	QTB_CUDA(cudaGetLastError());
