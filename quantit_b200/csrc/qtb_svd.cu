@@ -1112,7 +1112,7 @@ constexpr int kPanelInner = 1;      // inner sweeps per visit (measured: 1 beats
 __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup *__restrict__ groups,
                                                                    const SvdItem *__restrict__ items,
                                                                    double *__restrict__ X, unsigned long long *offmax,
-                                                                   int panel_inner)
+                                                                   int panel_inner, int cross_only)
 {
 	extern __shared__ double sp[];
 	__shared__ int s_rot;
@@ -1123,31 +1123,61 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 	const int ld = nrows | 1; // odd leading dimension: lanes walking a column never collide, columns are skewed
 	double *Xg = X + G.x_off;
 	auto gcol = [&](int c) { return c < wi ? it.bi * G.jb + c : it.bj * G.jb + (c - wi); };
-	for (int e = threadIdx.x; e < p * nrows; e += blockDim.x)
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+	// panel load: a warp per column, 8 independent loads in flight per lane (the flat e / nrows loop of the first version
+	// serialised one global-load latency per element: ~6 us of a ~20 us visit at bond dimension 256)
+	for (int c = warp; c < p; c += nwarps)
 	{
-		const int c = e / nrows, r = e - c * nrows;
-		sp[c * ld + r] = Xg[(i64)gcol(c) * G.ld + r];
+		const double *src = Xg + (i64)gcol(c) * G.ld;
+		double *dst = sp + c * ld;
+		int r = lane;
+		for (; r + 7 * 32 < nrows; r += 8 * 32)
+		{
+			double v[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				v[u] = src[r + u * 32];
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				dst[r + u * 32] = v[u];
+		}
+		for (; r < nrows; r += 32)
+			dst[r] = src[r];
 	}
 	if (threadIdx.x == 0)
 		s_rot = 0;
 	__syncthreads();
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int pe = (p + 1) & ~1;
 	double worst = 0.0;
 	const double rot_tol = 2.3e-16 * sqrt((double)G.m);
 	const double rot_tol2 = rot_tol * rot_tol;
 	// a panel that holds the whole matrix is driven to convergence here; otherwise a few inner sweeps per visit
 	const int max_inner = (G.nb <= 2) ? 30 : panel_inner;
+	// cross-only visits (groups of more than two column blocks): a visit of the block pair (bi, bj) rotates only the
+	// wi x wj pairs with one column in each block, max(wi, wj) rounds instead of the wi + wj - 1 of the full round
+	// robin; the pairs inside a block are rotated once per sweep by the diagonal items (bi, nb) of a separate launch.
+	// Every column pair is then visited once per sweep (plain cyclic Jacobi by pairs) instead of the within-block pairs
+	// being redone at every one of the block's nb - 1 visits.
+	const bool cross = cross_only && G.nb > 2 && wj > 0;
+	const int wmax = max(wi, wj);
+	const int nround = cross ? wmax : pe - 1, npair = cross ? wmax : pe / 2;
 	for (int sweep = 0; sweep < max_inner; ++sweep)
 	{
-		for (int step = 0; step < pe - 1; ++step)
+		for (int step = 0; step < nround; ++step)
 		{
 			// pair pw of the round belongs to warp pw mod 32 (panels wider than 64 columns — whole small groups — give a
 			// warp two or more disjoint pairs per round)
-			for (int pw = warp; pw < pe / 2; pw += blockDim.x / 32)
+			for (int pw = warp; pw < npair; pw += blockDim.x / 32)
 			{
 				int a, b;
-				if (pw == 0)
+				if (cross)
+				{ // column pw of block bi with column (pw + step) mod wmax of block bj
+					a = pw < wi ? pw : p;
+					b = pw + step;
+					b = b >= wmax ? b - wmax : b;
+					b = b < wj ? wi + b : p;
+				}
+				else if (pw == 0)
 				{
 					a = pe - 1;
 					b = step;
@@ -1224,10 +1254,13 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 			s_rot = 0;
 		__syncthreads();
 	}
-	for (int e = threadIdx.x; e < p * nrows; e += blockDim.x)
+	for (int c = warp; c < p; c += nwarps)
 	{
-		const int c = e / nrows, r = e - c * nrows;
-		Xg[(i64)gcol(c) * G.ld + r] = sp[c * ld + r];
+		double *dstg = Xg + (i64)gcol(c) * G.ld;
+		const double *srcs = sp + c * ld;
+#pragma unroll 4
+		for (int r = lane; r < nrows; r += 32)
+			dstg[r] = srcs[r];
 	}
 	if (lane == 0 && worst > 0.0)
 		atomicMax(offmax, (unsigned long long)__double_as_longlong(worst));
@@ -2017,6 +2050,8 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			// small panels: 32 jb threads, so that several panels share an SM; large panels (<= 2 per SM anyway): a full
 			// CTA, the extra warps speed up the panel load / store
 			const int panel_threads = panel_smem <= 56 * 1024 ? std::max(64, std::min(kPanelThreads, 32 * jb)) : kPanelThreads;
+			static const bool panel_cross_env = !(std::getenv("QTB_SVD_PANEL_CROSS") && std::atoi(std::getenv("QTB_SVD_PANEL_CROSS")) == 0);
+			const bool panel_cross = use_panel && panel_cross_env;
 			static const int panel_inner = std::getenv("QTB_SVD_PANEL_INNER") ? std::atoi(std::getenv("QTB_SVD_PANEL_INNER")) : kPanelInner;
 			static const int inner_max = std::getenv("QTB_SVD_INNER") ? std::atoi(std::getenv("QTB_SVD_INNER")) : 4;
 			// inner sweeps stop once the off-diagonal mass they leave (~ g^2) is below inner_tol x the pair's gauge
@@ -2095,7 +2130,9 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					max_m_l = std::max(max_m_l, dg[g].m);
 				}
 				L.nch_max = (max_m_l + kGramRows - 1) / kGramRows;
-				L.step_begin.assign(L.period + 1, 0);
+				// shared-memory panel path with cross-only visits: step `period` of the schedule is the diagonal launch (one
+				// item per column block of every group with more than two blocks), run first in every sweep
+				L.step_begin.assign(L.period + 2, 0);
 				for (int t = 0; t < L.period; ++t)
 				{
 					L.step_begin[t] = (int)L.items.size();
@@ -2124,12 +2161,18 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					}
 				}
 				L.step_begin[L.period] = (int)L.items.size();
+				if (panel_cross)
+					for (i64 g : L.groups)
+						if (mine(g) && dg[g].nb > 2)
+							for (int bi = 0; bi < dg[g].nb; ++bi)
+								L.items.push_back({(int)g, bi, bi});
+				L.step_begin[L.period + 1] = (int)L.items.size();
 				// single-block groups use item (g,0,0): the panel is the block itself. block_width(bj) would double count,
 				// so encode bj = nb (an empty block) instead.
 				for (auto &it : L.items)
 					if (it.bi == it.bj)
 						it.bj = dg[it.group].nb; // width = min(jb, n - nb*jb) <= 0 -> clamp in kernels
-				for (int t = 0; t < L.period; ++t)
+				for (int t = 0; t <= L.period; ++t)
 					L.max_items = std::max(L.max_items, L.step_begin[t + 1] - L.step_begin[t]);
 				if (L.max_items == 0)
 				{
@@ -2177,15 +2220,17 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					Lane &L = lanes[l];
 					if (!L.active || L.max_items == 0)
 						continue;
-					for (int t = 0; t < L.period; ++t)
+					for (int tt = -1; tt < L.period; ++tt)
 					{
+						const int t = tt < 0 ? L.period : tt; // the diagonal launch first
 						const int cnt = L.step_begin[t + 1] - L.step_begin[t];
 						if (cnt == 0)
 							continue;
 						const SvdItem *its = L.d_items + L.step_begin[t];
 						if (use_panel)
 						{
-							svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner);
+							svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, its, X, L.d_off + sweep, panel_inner,
+							                                                             (int)panel_cross);
 							ctx.counters[0] += 1;
 							continue;
 						}
