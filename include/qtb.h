@@ -55,6 +55,12 @@ qtb_status qtb_ctx_sync(qtb_ctx *ctx);
 /* returns the engine's cached (free) device blocks to the driver; live tensors are untouched. The reference has no
  * counterpart (libtorch's CUDA caching allocator: c10::cuda::CUDACachingAllocator::emptyCache()). */
 qtb_status qtb_ctx_trim(qtb_ctx *ctx);
+/* Where the block-pair matching of a contraction runs (the two-pointer merge over "columns" of btensor::tensordot,
+ * sources/btensor.cpp:2057-2108): mode 0 = host sort, 1 = device sort / segmented-match kernels (qtb_match.cu),
+ * -1 (default) = by size (device from 8192 blocks on). The plan — output block set, pair order — is identical either
+ * way. qtb_ctx_device_matches: how many plans of this context were matched on the device. */
+qtb_status qtb_ctx_set_device_planner(qtb_ctx *ctx, int mode);
+qtb_status qtb_ctx_device_matches(qtb_ctx *ctx, int64_t *count);
 void *qtb_ctx_stream(qtb_ctx *ctx);
 /* counters since context creation: [0] kernel launches of this library, [1] grouped-GEMM launches,
  * [2] plans built, [3] plan-cache hits, [4] bytes host->device, [5] bytes device->host,

@@ -145,6 +145,19 @@ qtb_status qtb_ctx_sync(qtb_ctx *ctx)
 {
 	return guarded(ctx, [&]() { QTB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
 }
+qtb_status qtb_ctx_set_device_planner(qtb_ctx *ctx, int mode)
+{
+	return guarded(ctx,
+	    [&]()
+	    {
+		    QTB_REQUIRE(mode >= -1 && mode <= 1, QTB_ERR_INVALID_ARGUMENT, "device planner mode must be -1, 0 or 1");
+		    ctx->c.planner_mode = mode;
+	    });
+}
+qtb_status qtb_ctx_device_matches(qtb_ctx *ctx, int64_t *count)
+{
+	return guarded(ctx, [&]() { *count = ctx->c.device_matches; });
+}
 qtb_status qtb_ctx_trim(qtb_ctx *ctx)
 {
 	return guarded(ctx, [&]() { ctx->c.trim_cache(); });

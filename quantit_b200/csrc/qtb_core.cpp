@@ -981,17 +981,56 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 			key = key * (u128)std::max<i64>(t.st.nsec[d], 1) + (u128)t.idx(blk)[d];
 		return key;
 	};
-	std::vector<std::pair<u128, i64>> b_sorted(b.nblocks);
-	for (i64 j = 0; j < b.nblocks; ++j)
-		b_sorted[j] = {encode(b, j, dims_b, 0), j};
-	std::sort(b_sorted.begin(), b_sorted.end());
 	struct Cand
 	{
 		u128 okey, ckey;
 		i64 a, b;
 	};
 	std::vector<Cand> cands;
-	for (i64 i = 0; i < a.nblocks; ++i)
+	// device matching (qtb_match.cu) when asked for, or by size; needs every key below 2^63
+	bool on_device = false;
+	{
+		const int mode = ctx.planner_mode;
+		const bool want = mode == 1 || (mode < 0 && a.nblocks + b.nblocks >= 8192);
+		u128 rc = 1, rfa = 1, rfb = 1;
+		for (i64 c = 0; c < k; ++c)
+			rc *= (u128)std::max<i64>(b.st.nsec[dims_b[c]], 1);
+		for (auto d : free_a)
+			rfa *= (u128)std::max<i64>(a.st.nsec[d], 1);
+		for (auto d : free_b)
+			rfb *= (u128)std::max<i64>(b.st.nsec[d], 1);
+		const u128 lim = (u128)1 << 62;
+		if (want && rc < lim && rfa * rfb < lim && rfa < lim && rfb < lim && a.nblocks < (i64(1) << 30) && b.nblocks < (i64(1) << 30))
+		{
+			std::vector<unsigned long long> a_ck(a.nblocks), a_fk(a.nblocks), b_ck(b.nblocks), b_fk(b.nblocks);
+			for (i64 i = 0; i < a.nblocks; ++i)
+			{
+				u128 ck = 0;
+				for (i64 c = 0; c < k; ++c)
+					ck = ck * (u128)std::max<i64>(b.st.nsec[dims_b[c]], 1) + (u128)a.idx(i)[dims_a[c]];
+				a_ck[i] = (unsigned long long)ck;
+				a_fk[i] = (unsigned long long)encode(a, i, free_a, 0);
+			}
+			for (i64 j = 0; j < b.nblocks; ++j)
+			{
+				b_ck[j] = (unsigned long long)encode(b, j, dims_b, 0);
+				b_fk[j] = (unsigned long long)encode(b, j, free_b, 0);
+			}
+			std::vector<MatchRec> recs;
+			if (device_match(ctx, a_ck, a_fk, b_ck, b_fk, (unsigned long long)rfb, recs))
+			{
+				on_device = true;
+				cands.reserve(recs.size());
+				for (auto &r : recs)
+					cands.push_back({(u128)r.okey, (u128)r.ckey, (i64)r.a, (i64)r.b});
+			}
+		}
+	}
+	std::vector<std::pair<u128, i64>> b_sorted(on_device ? 0 : b.nblocks);
+	for (i64 j = 0; j < b.nblocks && !on_device; ++j)
+		b_sorted[j] = {encode(b, j, dims_b, 0), j};
+	std::sort(b_sorted.begin(), b_sorted.end());
+	for (i64 i = 0; i < a.nblocks && !on_device; ++i)
 	{
 		// contracted key in B's radices (section counts of contracted dims agree, checked above)
 		u128 ck = 0;
@@ -1004,8 +1043,9 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 		for (auto it = lo; it != b_sorted.end() && it->first == ck; ++it)
 			cands.push_back({encode(b, it->second, free_b, ka), ck, i, it->second});
 	}
-	std::sort(cands.begin(), cands.end(),
-	          [](const Cand &x, const Cand &y) { return x.okey != y.okey ? x.okey < y.okey : x.ckey < y.ckey; });
+	if (!on_device)
+		std::sort(cands.begin(), cands.end(),
+		          [](const Cand &x, const Cand &y) { return x.okey != y.okey ? x.okey < y.okey : x.ckey < y.ckey; });
 
 	lap(1);
 	// ---- operand offset tables (the fused permute_bl, btensor.cpp:1843-1894) ----

@@ -193,6 +193,15 @@ QTB_HD inline void gemm_warp_grid(int mv, int nv, int &gm, int &gn, int &am, int
 	}
 }
 
+// one candidate pair of the device matching (qtb_match.cu), sorted by (okey, ckey); head = 1: first pair of an output block
+struct MatchRec
+{
+	unsigned long long okey, ckey;
+	int32_t a, b;
+	int32_t head, pad;
+};
+static_assert(sizeof(MatchRec) == 32, "MatchRec is copied back as packed 32-byte records");
+
 struct GemmTile
 { // one work item of the grouped GEMM: a tile of one output block, self-contained (the kernels fetch ONE descriptor per
   // item, no dependent second fetch of the block's record)
@@ -293,6 +302,8 @@ struct Ctx
 	cudaMemPool_t pool = nullptr;
 	int sm_count = 148;
 	i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int planner_mode = -1;  // block-pair matching: 0 host, 1 device (qtb_match.cu), -1 by size (qtb_ctx_set_device_planner)
+	i64 device_matches = 0; // contractions whose pairs were matched by the device kernels
 	std::unordered_map<uint64_t, std::shared_ptr<Plan>> plan_cache;
 	std::shared_ptr<PlanSlab> plan_slab; // the slab new plan tables are carved from
 	// live arenas: a context that is destroyed before its tensors orphans them (Arena::ctx = nullptr, the device block is
@@ -377,6 +388,10 @@ std::unique_ptr<Tensor> contiguous(Ctx &ctx, const Tensor &t); // packed copy (g
 
 // kernels (qtb_gemm.cu / qtb_vec.cu)
 // cin != nullptr: c = alpha * cin + beta * (a . b), cin laid out like the output (the tensorgdot epilogue)
+// device block-pair matching (qtb_match.cu); false = input beyond what the kernels hold, use the host path
+bool device_match(Ctx &ctx, const std::vector<unsigned long long> &a_ck, const std::vector<unsigned long long> &a_fk,
+                  const std::vector<unsigned long long> &b_ck, const std::vector<unsigned long long> &b_fk,
+                  unsigned long long rb, std::vector<MatchRec> &out);
 void launch_grouped_gemm(Ctx &ctx, const Plan &plan, const double *a, const double *b, double *c,
                          const Plan::Owned *owned = nullptr, const double *cin = nullptr, double alpha = 0.0,
                          double beta = 1.0);

@@ -1194,12 +1194,36 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 				{
 					double *x = sp + ci * ld, *y = sp + cj * ld;
 					double al = 0.0, be = 0.0, ga = 0.0;
-					for (int r = lane; r < G.m; r += 32)
-					{
-						const double xv = x[r], yv = y[r];
-						al += xv * xv;
-						be += yv * yv;
-						ga += xv * yv;
+					{ // two independent accumulator sets, four rows in flight per lane: the loop is a latency chain
+						double al2 = 0.0, be2 = 0.0, ga2 = 0.0;
+						int r = lane;
+						for (; r + 96 < G.m; r += 128)
+						{
+							const double x0 = x[r], y0 = y[r], x1 = x[r + 32], y1 = y[r + 32];
+							const double x2 = x[r + 64], y2 = y[r + 64], x3 = x[r + 96], y3 = y[r + 96];
+							al += x0 * x0;
+							be += y0 * y0;
+							ga += x0 * y0;
+							al2 += x1 * x1;
+							be2 += y1 * y1;
+							ga2 += x1 * y1;
+							al += x2 * x2;
+							be += y2 * y2;
+							ga += x2 * y2;
+							al2 += x3 * x3;
+							be2 += y3 * y3;
+							ga2 += x3 * y3;
+						}
+						for (; r < G.m; r += 32)
+						{
+							const double xv = x[r], yv = y[r];
+							al += xv * xv;
+							be += yv * yv;
+							ga += xv * yv;
+						}
+						al += al2;
+						be += be2;
+						ga += ga2;
 					}
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1)
@@ -1234,12 +1258,30 @@ __global__ void __launch_bounds__(kPanelThreads) svd_panel_kernel(const SvdGroup
 					const bool swap = ((cs * cs - sn * sn) * (al - be) - 4.0 * cs * sn * ga) < 0.0;
 					if (rot || swap)
 					{
-						for (int r = lane; r < nrows; r += 32)
+						const double c1 = swap ? sn : cs, s1 = swap ? cs : -sn; // x' = c1 x + s1 y
+						const double c2 = swap ? cs : sn, s2 = swap ? -sn : cs; // y' = c2 x + s2 y
+						int r = lane;
+						for (; r + 96 < nrows; r += 128)
+						{
+							double xv[4], yv[4];
+#pragma unroll
+							for (int u = 0; u < 4; ++u)
+							{
+								xv[u] = x[r + 32 * u];
+								yv[u] = y[r + 32 * u];
+							}
+#pragma unroll
+							for (int u = 0; u < 4; ++u)
+							{
+								x[r + 32 * u] = c1 * xv[u] + s1 * yv[u];
+								y[r + 32 * u] = c2 * xv[u] + s2 * yv[u];
+							}
+						}
+						for (; r < nrows; r += 32)
 						{
 							const double xv = x[r], yv = y[r];
-							const double xn = cs * xv - sn * yv, yn = sn * xv + cs * yv;
-							x[r] = swap ? yn : xn;
-							y[r] = swap ? xn : yn;
+							x[r] = c1 * xv + s1 * yv;
+							y[r] = c2 * xv + s2 * yv;
 						}
 					}
 				}

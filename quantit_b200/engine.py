@@ -72,6 +72,8 @@ _SIGS = [
     ("qtb_ctx_destroy", None, [vp]),
     ("qtb_ctx_sync", C.c_int, [vp]),
     ("qtb_ctx_trim", C.c_int, [vp]),
+    ("qtb_ctx_set_device_planner", C.c_int, [vp, C.c_int]),
+    ("qtb_ctx_device_matches", C.c_int, [vp, p_i64]),
     ("qtb_ctx_stream", vp, [vp]),
     ("qtb_ctx_counters", C.c_int, [vp, p_i64]),
     ("qtb_ctx_set_sharding", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -203,6 +205,16 @@ class Context:
     def trim_cache(self) -> None:
         """return the engine's cached free device blocks to the driver (qtb_ctx_trim)"""
         _check(self.lib.qtb_ctx_trim(self.h))
+
+    def set_device_planner(self, mode: int) -> None:
+        """where the block-pair matching of a contraction runs: 0 host, 1 device kernels, -1 by size
+        (qtb_ctx_set_device_planner; reference btensor.cpp:2057-2108)"""
+        _check(self.lib.qtb_ctx_set_device_planner(self.h, int(mode)))
+
+    def device_matches(self) -> int:
+        out = (C.c_int64 * 1)()
+        _check(self.lib.qtb_ctx_device_matches(self.h, out))
+        return int(out[0])
 
     @property
     def stream(self) -> int:
