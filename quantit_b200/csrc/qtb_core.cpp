@@ -1387,7 +1387,11 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 		ctx.plan_cache.clear();
 	auto p = build_plan(ctx, a, b, dims_a, dims_b);
 	p->key2 = h2;
-	ctx.plan_cache[h] = p;
+	// adopted operands (qtb_tensor_adopt): the block offsets are the pointer deltas of separately allocated caller
+	// blocks, different at every call — such a plan would never be hit again, so it is not kept
+	const bool adopted = (a.arena && !a.arena->owned) || (b.arena && !b.arena->owned);
+	if (!adopted)
+		ctx.plan_cache[h] = p;
 	return p;
 }
 
