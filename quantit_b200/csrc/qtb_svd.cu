@@ -71,6 +71,8 @@ struct ScatterDesc
 	int rows, kept, ld, group;
 	int normalize; // 1: divide column j by sigma_j (the A part), 0: take as is (the rotation part)
 	int perm_off;  // offset of this group's column permutation / sigma list
+	int rmap_off;  // >= 0: row r of the block is row rowmap[rmap_off + r] of X_g (column pre-sort of the QR path), else -1
+	int pad;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1331,10 +1333,37 @@ __global__ void __launch_bounds__(128) svd_norm_kernel(const SvdGroup *__restric
 	}
 }
 
+// Column pre-sort of the QR path. The theta of a DMRG update is column graded (one bond carries the singular values of
+// the previous update: column norms over 7 decades at bond dimension 160); Householder QR without pivoting of such a
+// matrix leaves R far from diagonally dominant. Sorting the columns by decreasing norm first gives most of what column
+// pivoting would (numpy model of this iteration on a real theta', profiles/r2: 8 -> 5 block-Jacobi sweeps, 66 -> 36 pair
+// visits; true QRCP: 5 sweeps, 33 visits) for two streaming passes over F.
+struct PreSortDesc
+{
+	i64 a_off, u_off; // F_g (m x n, ld = m) and the same-size scratch (the U workspace, free until the Jacobi iteration ends)
+	int m, n, sig_off, pad;
+};
+// mode 0: scratch(:, j) = F(:, perm[j]); colpos[perm[j]] = j.   mode 1: F = scratch
+__global__ void presort_cols_kernel(const PreSortDesc *__restrict__ descs, double *__restrict__ X, const int *__restrict__ perm,
+                                    int *__restrict__ colpos, int mode)
+{
+	const PreSortDesc d = descs[blockIdx.y];
+	for (int j = blockIdx.x; j < d.n; j += gridDim.x)
+	{
+		const int src_col = mode == 0 ? perm[d.sig_off + j] : j;
+		const double *src = X + (mode == 0 ? d.a_off : d.u_off) + (i64)src_col * d.m;
+		double *dst = X + (mode == 0 ? d.u_off : d.a_off) + (i64)j * d.m;
+		for (int r = threadIdx.x; r < d.m; r += blockDim.x)
+			dst[r] = src[r];
+		if (mode == 0 && threadIdx.x == 0)
+			colpos[d.sig_off + src_col] = j;
+	}
+}
+
 // U / V blocks: dst[r, j] = X(row0 + r, perm[j]) (/ sigma[perm[j]])
 __global__ void svd_scatter_kernel(const ScatterDesc *__restrict__ descs, int ndesc, const double *__restrict__ X,
                                    const int *__restrict__ perm, const double *__restrict__ sigma,
-                                   double *__restrict__ dst)
+                                   double *__restrict__ dst, const int *__restrict__ rowmap)
 {
 	for (int b = blockIdx.y; b < ndesc; b += gridDim.y)
 	{
@@ -1344,7 +1373,8 @@ __global__ void svd_scatter_kernel(const ScatterDesc *__restrict__ descs, int nd
 		{
 			const int r = (int)(e % d.rows), j = (int)(e / d.rows); // consecutive threads walk a column of X (coalesced)
 			const int col = perm[d.perm_off + j];
-			double v = X[d.src_off + r + (i64)col * d.ld];
+			const int rs = d.rmap_off >= 0 ? rowmap[d.rmap_off + r] : r;
+			double v = X[d.src_off + rs + (i64)col * d.ld];
 			if (d.normalize)
 			{
 				const double s = sigma[d.perm_off + col];
@@ -1883,8 +1913,12 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	static const bool devsel_env = !(std::getenv("QTB_SVD_DEVSEL") && std::atoi(std::getenv("QTB_SVD_DEVSEL")) == 0);
 	const bool debug_census = std::getenv("QTB_SVD_DEBUG") && std::atoi(std::getenv("QTB_SVD_DEBUG")) >= 2;
 	const bool dev_select = devsel_env && !eigh_mode && ng > 0 && sig_total > 0 && sig_total <= 16384 && cols_all_max <= 8192;
-	int *d_perm_dev = nullptr, *d_sel = nullptr;
+	int *d_perm_dev = nullptr, *d_sel = nullptr, *d_colpos = nullptr;
 	double *d_sorted = nullptr;
+	// column pre-sort before the QR (presort_cols_kernel); groups of one column and eigh (every column norm is dominated by
+	// the shift) have nothing to gain
+	static const bool presort_env = !(std::getenv("QTB_SVD_PRESORT") && std::atoi(std::getenv("QTB_SVD_PRESORT")) == 0);
+	const bool presort = presort_env && use_qr && !eigh_mode && sig_total > 0 && cols_all_max <= 8192;
 	std::vector<int> sel_host;
 	// QTB_SVD_DEBUG >= 2: wall-clock split of this call (each mark synchronises the stream)
 	double phase_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -1987,6 +2021,49 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			QTB_CUDA(cudaGetLastError());
 			ctx_free(ctx, d_em);
 			ctx.counters[0] += 3;
+		}
+		// ---- column pre-sort of F by decreasing norm (QR path) ----
+		if (presort)
+		{
+			std::vector<SvdGroup> fg(ng);
+			std::vector<PreSortDesc> pd;
+			for (i64 g = 0; g < ng; ++g)
+			{
+				fg[g] = dg[g];
+				fg[g].x_off = qg[g].a_off;
+				fg[g].m = (int)fm[g];
+				fg[g].ld = (int)fm[g];
+				if (mine(g) && dg[g].n > 1)
+					pd.push_back({qg[g].a_off, qg[g].u_off, (int)fm[g], dg[g].n, sig_off[g], 0});
+			}
+			d_colpos = (int *)ctx_alloc(ctx, (size_t)sig_total * sizeof(int));
+			if (!pd.empty())
+			{
+				auto d_fg = (SvdGroup *)ctx_upload(ctx, fg.data(), fg.size() * sizeof(SvdGroup));
+				auto d_pd = (PreSortDesc *)ctx_upload(ctx, pd.data(), pd.size() * sizeof(PreSortDesc));
+				double *d_pnorm = (double *)ctx_alloc(ctx, (size_t)sig_total * sizeof(double));
+				double *d_psorted = (double *)ctx_alloc(ctx, (size_t)sig_total * sizeof(double));
+				int *d_pperm = (int *)ctx_alloc(ctx, (size_t)sig_total * sizeof(int));
+				int n2max = 1;
+				while (n2max < cols_all_max)
+					n2max <<= 1;
+				if (ctx.attr_once(6))
+				{
+					QTB_CUDA(cudaFuncSetAttribute(svd_sector_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+					QTB_CUDA(cudaFuncSetAttribute(svd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+				}
+				svd_norm_kernel<<<dim3(64, (unsigned)ng), 128, 0, ctx.stream>>>(d_fg, d_sigoff, X, d_pnorm);
+				svd_sector_sort_kernel<<<(unsigned)ng, 1024, (size_t)n2max * 12, ctx.stream>>>(d_fg, d_sigoff, d_pnorm, d_pperm, d_psorted);
+				presort_cols_kernel<<<dim3(128, (unsigned)pd.size()), 256, 0, ctx.stream>>>(d_pd, X, d_pperm, d_colpos, 0);
+				presort_cols_kernel<<<dim3(128, (unsigned)pd.size()), 256, 0, ctx.stream>>>(d_pd, X, d_pperm, d_colpos, 1);
+				QTB_CUDA(cudaGetLastError());
+				ctx.counters[0] += 4;
+				ctx_free(ctx, d_fg);
+				ctx_free(ctx, d_pd);
+				ctx_free(ctx, d_pnorm);
+				ctx_free(ctx, d_psorted);
+				ctx_free(ctx, d_pperm);
+			}
 		}
 		mark(0);
 		// ---- QR preconditioning: F = Q R (blocked Householder), X = [R^T ; I] ----
@@ -2732,6 +2809,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			const UB &e = tab[pos];
 			const HostGroup &hg = groups[e.group];
 			ScatterDesc s{};
+			s.rmap_off = -1;
 			s.dst_off = T->offs[k];
 			i64 rows = 1;
 			for (i64 d = 0; d < tr - 1; ++d)
@@ -2749,6 +2827,11 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 				s.normalize = in_a_part ? 0 : 1;
 				s.ld = in_a_part ? (int)fm[e.group] : dg[e.group].ld;
 				s.src_off = (in_a_part ? qg[e.group].u_off : dg[e.group].x_off) + e.off_in_group;
+				if (!in_a_part && presort && dg[e.group].n > 1)
+				{ // the rows of W are in pre-sorted column order: row (off + r) of the block is row colpos[off + r]
+					s.src_off = dg[e.group].x_off;
+					s.rmap_off = sig_off[e.group] + (int)e.off_in_group;
+				}
 			}
 			else
 			{
@@ -2766,7 +2849,7 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 			auto d_perm = dev_select ? (void *)d_perm_dev : ctx_upload(ctx, perm.data(), perm.size() * sizeof(int));
 			dim3 grid(8, (unsigned)std::min<size_t>(sd.size(), 4096));
 			svd_scatter_kernel<<<grid, 256, 0, ctx.stream>>>((const ScatterDesc *)d_sd, (int)sd.size(), X, (const int *)d_perm,
-			                                                d_sigma, T->arena->ptr);
+			                                                d_sigma, T->arena->ptr, d_colpos);
 			QTB_CUDA(cudaGetLastError());
 			ctx_free(ctx, d_sd);
 			if (!dev_select)
@@ -2781,6 +2864,8 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 	build(U, 0, split, false, a.st.sel, ub, u_alive, true);
 	if (!eigh_mode)
 		build(V, split, r, true, neutral, vb, v_alive, false);
+	if (d_colpos)
+		ctx_free(ctx, d_colpos);
 	if (d_perm_dev)
 	{
 		ctx_free(ctx, d_perm_dev);

@@ -427,15 +427,16 @@ __global__ void __launch_bounds__(256) qr_rt_kernel(const QrGroup *__restrict__ 
 	}
 }
 
-// U(0:n, :) = J (the rotations accumulated under R^T); the rows below stay zero.  grid = (column chunks, groups)
+// U(0:n, :) = J (the rotations accumulated under R^T), the rows below zero (written here: the U workspace doubles as the
+// scratch of the column pre-sort).  grid = (column chunks, groups)
 __global__ void __launch_bounds__(256) qr_j_kernel(const QrGroup *__restrict__ groups, double *__restrict__ ws)
 {
 	const QrGroup G = groups[blockIdx.y];
 	const double *Xg = ws + G.x_off;
 	double *Ug = ws + G.u_off;
 	for (int c = blockIdx.x; c < G.n; c += gridDim.x)
-		for (int r = threadIdx.x; r < G.n; r += 256)
-			Ug[(i64)c * G.m + r] = Xg[(i64)c * (2 * G.n) + G.n + r];
+		for (int r = threadIdx.x; r < G.m; r += 256)
+			Ug[(i64)c * G.m + r] = r < G.n ? Xg[(i64)c * (2 * G.n) + G.n + r] : 0.0;
 }
 
 } // namespace
