@@ -2331,6 +2331,16 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					QTB_CUDA(cudaStreamWaitEvent(lanes[l].stream, ctx.aux_events[nlanes], 0));
 			}
 			unsigned long long *h_gauge = ctx.pinned_gauge(); // pinned: the read-back of one lane must not block the host
+			// Shared-memory panel path: the launches of one sweep (diagonal launch + one per round-robin step, 17 us each at
+			// bond dimension 256, a third of it launch latency) are identical from sweep to sweep, so they are captured once
+			// per call into a CUDA graph and replayed — one graph launch per sweep instead of ~17 kernel launches.
+			static const bool graph_env = !(std::getenv("QTB_SVD_GRAPH") && std::atoi(std::getenv("QTB_SVD_GRAPH")) == 0);
+			int panel_steps = 0;
+			if (use_panel)
+				for (int t = 0; t <= lanes[0].period; ++t)
+					panel_steps += lanes[0].step_begin[t + 1] > lanes[0].step_begin[t];
+			const bool use_graph = use_panel && graph_env && nlanes == 1 && panel_steps >= 4;
+			cudaGraphExec_t panel_exec = nullptr;
 			for (int sweep = 0; sweep < kMaxSweeps; ++sweep)
 			{
 				bool any = false;
@@ -2339,6 +2349,30 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 					Lane &L = lanes[l];
 					if (!L.active || L.max_items == 0)
 						continue;
+					if (use_graph)
+					{
+						if (!panel_exec)
+						{
+							cudaGraph_t graph = nullptr;
+							QTB_CUDA(cudaStreamBeginCapture(L.stream, cudaStreamCaptureModeThreadLocal));
+							cudaMemsetAsync(L.d_off, 0, sizeof(unsigned long long), L.stream); // the sweep's gauge slot
+							for (int tt = -1; tt < L.period; ++tt)
+							{
+								const int t = tt < 0 ? L.period : tt;
+								const int cnt = L.step_begin[t + 1] - L.step_begin[t];
+								if (cnt > 0)
+									svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, L.d_items + L.step_begin[t], X,
+									                                                             L.d_off, panel_inner, (int)panel_cross);
+							}
+							QTB_CUDA(cudaStreamEndCapture(L.stream, &graph));
+							QTB_CUDA(cudaGraphInstantiate(&panel_exec, graph, 0));
+							QTB_CUDA(cudaGraphDestroy(graph));
+						}
+						QTB_CUDA(cudaGraphLaunch(panel_exec, L.stream));
+						ctx.counters[0] += panel_steps;
+						QTB_CUDA(cudaMemcpyAsync(h_gauge + l, L.d_off, sizeof(unsigned long long), cudaMemcpyDeviceToHost, L.stream));
+						continue;
+					}
 					for (int tt = -1; tt < L.period; ++tt)
 					{
 						const int t = tt < 0 ? L.period : tt; // the diagonal launch first
@@ -2454,6 +2488,8 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 				if (!any)
 					break;
 			}
+			if (panel_exec)
+				QTB_CUDA(cudaGraphExecDestroy(panel_exec));
 			// join: what follows on the context's stream (column norms, scatter) sees every lane's result
 			for (int l = 0; l < nlanes && nlanes > 1; ++l)
 			{
