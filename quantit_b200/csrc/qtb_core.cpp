@@ -1302,7 +1302,10 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 					{ // 64 x 64: the four warps share the valid 8x8 atoms of the tile (gemm_warp_grid)
 						int gm, gn, am, an;
 						gemm_warp_grid(std::min(8, (int)(o.M - m0 + 7) / 8), std::min(8, (int)(o.N - n0 + 7) / 8), gm, gn, am, an);
-						c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * am * an);
+						static const double cT0 = std::getenv("QTB_COST_T0") ? std::atof(std::getenv("QTB_COST_T0")) : 800.0;
+						static const double cC0 = std::getenv("QTB_COST_C0") ? std::atof(std::getenv("QTB_COST_C0")) : 150.0;
+						static const double cA = std::getenv("QTB_COST_A") ? std::atof(std::getenv("QTB_COST_A")) : 16.0;
+						c = cT0 + (double)nchunks * (cC0 + cA * (BKc / 4) * am * an);
 					}
 					else // 128 x 128: the busiest consumer warp always computes its whole warp tile (unpredicated path)
 						c = 800.0 + (double)nchunks * (150.0 + 16.0 * (BKc / 4) * (wm / 8) * (wn / 8));
