@@ -542,7 +542,7 @@ def main():
             hf["workload"] = "H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO): 3 block contractions"
             extra["heff_D4096"] = hf
             try:
-                extra["svd_sweep_hubbard"] = time_svd_sweep(torch, qb, ctx, [512, 1024, 2048, 4096])
+                extra["svd_sweep_hubbard"] = time_svd_sweep(torch, qb, ctx, [512, 1024, 2048, 4096, 8192])
             except Exception as e:  # noqa: BLE001
                 extra["svd_sweep_hubbard"] = {"error": repr(e)[:300]}
             for spec in [x for x in args.dmrg.split(";") if x.strip()]:
