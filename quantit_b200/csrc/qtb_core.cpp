@@ -1255,6 +1255,13 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	(void)n64;
 	// 128x128 tiles when they fill the machine and do not waste much on block edges
 	plan->tile_cfg = (n128 >= ctx.sm_count && pad128 <= 1.25 * pad64) ? 1 : 0;
+	// Sharded contexts: a rank runs 1 / world of the tiles. When that share is only a few tiles per SM, 128 x 128 tiles
+	// quantise badly (H_eff.psi at D=4096 on 8 ranks: 93 tiles for 148 SMs in the first contraction, 561 us against
+	// 330 ideal; profiles/r2/s62.txt) while the 64 x 64 configuration runs the same large-K products at the same rate
+	// (T2: 30.3 TFLOP/s with either, s63.txt) with four times the tiles. The arithmetic per output element is the same
+	// sequence of DMMAs in both configurations, so the result stays bit-identical to the single-GPU run.
+	if (plan->tile_cfg == 1 && ctx.world > 1 && n128 / ctx.world < 4 * (i64)ctx.sm_count)
+		plan->tile_cfg = 0;
 	if (const char *force = std::getenv("QTB_TILE")) // experiment switch: 64 / 128
 		plan->tile_cfg = std::atoi(force) == 128 ? 1 : 0;
 	// skinny: every product is [M x K].[K x N] with K, N <= 16 (contraction with the MPO): CUDA-core row kernel
@@ -1374,6 +1381,7 @@ std::shared_ptr<Plan> get_plan(Ctx &ctx, const Tensor &a, const Tensor &b, const
 		h = mix64(h, (uint64_t)d + 91);
 	// The cache is keyed by a 128-bit digest: `h` indexes the map, and a hit is only accepted when an independently mixed
 	// second digest of the same layouts (structure, charge type, block tables, offsets, dim lists) agrees as well.
+	h = mix64(h, (uint64_t)ctx.world + 977); // the tile configuration depends on the number of ranks
 	uint64_t h2 = mix64b(a.layout_hash2, b.layout_hash2 * 0x9e3779b97f4a7c15ull + 7);
 	h2 = mix64b(h2, dims_a.size());
 	for (auto d : dims_a)
