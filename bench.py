@@ -323,6 +323,39 @@ def time_heff(torch, qb, ctx, n_sec, D, sigma, steps, warmup, flush_buf, dist=No
             "launches_per_step": (c2["kernel_launches"] - c1["kernel_launches"]) / steps}
 
 
+def time_env_left(torch, qb, ctx, n_sec, D, sigma, steps, warmup, flush_buf):
+    """compute_left_env (reference dmrg.cpp:424-456: three block contractions E' = A^dag.(E.A).W) on the T3 shapes of SURVEY.md
+    section 8d; the site tensor A is the U factor of the two-site tensor's block SVD."""
+    from quantit_b200 import workloads as wl
+    psi, W, L, R = wl.heff_set(n_sec, D, sigma, seed=5)
+    bt = lambda d: qb.BTensor.from_host(**d, ctx=ctx)
+    Wb, l = bt(W), bt(L)
+    A, _, _ = qb.svd(bt(psi), 2, 1e-12, 4, D)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(warmup):
+        qb.compute_left_env(Wb, A, l)
+    ctx.sync()
+    c1 = ctx.counters()
+    evs = []
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = qb.compute_left_env(Wb, A, l)
+            e1.record(stream)
+            evs.append((e0, e1))
+            del out
+    ctx.sync()
+    torch.cuda.synchronize()
+    c2 = ctx.counters()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    flops = (c2["gemm_flops"] - c1["gemm_flops"]) / steps
+    return {"ms_per_step": ms, "flops_per_step": int(flops), "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "launches_per_step": (c2["kernel_launches"] - c1["kernel_launches"]) / steps,
+            "workload": f"compute_left_env at D={D} (T3 shapes: {n_sec} charge sectors, Heisenberg MPO): 3 block contractions"}
+
+
 def reference_dmrg_sweeps(L, maxbond, n_sweeps, cutoff, threads):
     """per-sweep wall milliseconds of the compiled reference's own dmrg() on the host CPU (oracle/_ref/ref_harness heis:
     its Heisenberg bMPO + its random bond-4 bMPS, same L / maximum_bond / cutoff, convergence_criterion 0). None when the
@@ -374,7 +407,7 @@ def time_dmrg_sweeps(qb, ctx, L, maxbond, n_sweeps, cutoff=1e-20, with_reference
 def time_svd_sweep(torch, qb, ctx, Ds, ref_max_D=1024):
     """T4 of SURVEY.md section 8d: svd(theta, 2, tol = 1e-10, min = 4, max = D) of a Hubbard-profile two-site tensor
     (U(1) x U(1), ~30-45 sectors per bond), D = 512 ... 8192; the compiled reference's svd on the host CPU beside it up to
-    ref_max_D. Wall time of the synchronous call (second of two calls)."""
+    ref_max_D. Wall time of the synchronous call (best of the second and third call; all three are listed)."""
     from quantit_b200 import workloads as wl
     out = {}
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
@@ -382,13 +415,13 @@ def time_svd_sweep(torch, qb, ctx, Ds, ref_max_D=1024):
         th = wl.hubbard_theta(D, np.random.default_rng(7))
         T = qb.BTensor.from_host(**th, ctx=ctx)
         ts = []
-        for _ in range(2):
+        for _ in range(3):
             ctx.sync()
             t0 = time.perf_counter()
             U, d, V = qb.svd(T, 2, 1e-10, 4, D)
             ctx.sync()
             ts.append(time.perf_counter() - t0)
-        rec = {"ms": ts[-1] * 1e3, "kept": int(sum(d.structure()[0][0])), "blocks": T.nblocks,
+        rec = {"ms": min(ts[1:]) * 1e3, "ms_calls": [t * 1e3 for t in ts], "kept": int(sum(d.structure()[0][0])), "blocks": T.nblocks,
                "bond_sectors": len(th["sec_sizes"][0]), "stored_MB": wl.stored_bytes(th) / 1e6}
         if D <= ref_max_D and os.path.exists(harness):
             with tempfile.TemporaryDirectory() as td:
@@ -541,6 +574,12 @@ def main():
             hf["roofline_frac"] = hf["value"] / peak
             hf["workload"] = "H_eff.psi at D=4096 (T3: 15 charge sectors, Heisenberg MPO): 3 block contractions"
             extra["heff_D4096"] = hf
+            try:
+                ev = time_env_left(torch, qb, ctx, 15, 4096, 1.6, 5, 3, flush_buf)
+                ev["roofline_frac"] = ev["value"] / peak
+                extra["env_left_D4096"] = ev
+            except Exception as e:  # noqa: BLE001
+                extra["env_left_D4096"] = {"error": repr(e)[:300]}
             try:
                 extra["svd_sweep_hubbard"] = time_svd_sweep(torch, qb, ctx, [512, 1024, 2048, 4096, 8192])
             except Exception as e:  # noqa: BLE001

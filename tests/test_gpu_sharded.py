@@ -108,6 +108,28 @@ def test_heff_env_svd_sharded_bit_identical(engine, world):
                 assert np.array_equal(o[name][1][k], blk), (name, k)
 
 
+def test_heff_sharded_bit_identical_across_tile_configurations(engine):
+    """at bond dimension 1536 the single-rank plans take 128 x 128 tiles while the plans of a sharded context take 64 x 64
+    (a rank's share of the large tiles would leave SMs idle); the per-element sequence of DMMAs is
+    the same, so H_eff.psi must still be bit-identical"""
+    qb = engine
+    psi, W, L, R = wl.heff_set(9, 1536, 1.6, seed=11)
+
+    def work(ctx, rank):
+        bt = lambda d: qb.BTensor.from_host(**d, ctx=ctx)
+        Wb = bt(W)
+        H2 = Wb.tensordot(Wb, [2], [0]).permute([0, 1, 3, 4, 2, 5])
+        phi = qb.hamil2site_times_state(bt(psi), H2, bt(L), bt(R))
+        return phi.structure(), phi.to_host()
+
+    ref = work(qb.Context(0), 0)
+    outs, _ = run_ranks(qb, 2, work)
+    for st, blocks in outs:
+        assert st == ref[0] and list(blocks) == list(ref[1])
+        for k, blk in ref[1].items():
+            assert np.array_equal(blocks[k], blk), k
+
+
 def test_dmrg_sharded_matches_reference_run(engine):
     """whole two-site DMRG (Heisenberg L=8, the committed reference run) on 2 sharded ranks: per-sweep energies equal
     the single-rank engine run bit for bit and the reference's to 1e-10"""
