@@ -1260,7 +1260,8 @@ static std::shared_ptr<Plan> build_plan(Ctx &ctx, const Tensor &a, const Tensor 
 	// 330 ideal; profiles/r2/s62.txt) while the 64 x 64 configuration runs the same large-K products at the same rate
 	// (T2: 30.3 TFLOP/s with either, s63.txt) with four times the tiles. The arithmetic per output element is the same
 	// sequence of DMMAs in both configurations, so the result stays bit-identical to the single-GPU run.
-	if (plan->tile_cfg == 1 && ctx.world > 1 && n128 / ctx.world < 4 * (i64)ctx.sm_count)
+	static const bool rule_single = std::getenv("QTB_TILE_RULE") && std::atoi(std::getenv("QTB_TILE_RULE")) == 1; // experiment
+	if (plan->tile_cfg == 1 && (ctx.world > 1 || rule_single) && n128 / ctx.world < 4 * (i64)ctx.sm_count)
 		plan->tile_cfg = 0;
 	if (const char *force = std::getenv("QTB_TILE")) // experiment switch: 64 / 128
 		plan->tile_cfg = std::atoi(force) == 128 ? 1 : 0;
