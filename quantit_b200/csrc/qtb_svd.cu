@@ -2364,9 +2364,17 @@ static void block_svd_impl(Ctx &ctx, const Tensor &a, i64 split, bool truncate, 
 									svd_panel_kernel<<<cnt, panel_threads, panel_smem, L.stream>>>(d_groups, L.d_items + L.step_begin[t], X,
 									                                                             L.d_off, panel_inner, (int)panel_cross);
 							}
-							QTB_CUDA(cudaStreamEndCapture(L.stream, &graph));
-							QTB_CUDA(cudaGraphInstantiate(&panel_exec, graph, 0));
-							QTB_CUDA(cudaGraphDestroy(graph));
+							// the capture is always ended (a stream left in capture mode would poison every later call on it)
+							const cudaError_t cap = cudaStreamEndCapture(L.stream, &graph);
+							if (cap != cudaSuccess || graph == nullptr)
+							{
+								if (graph)
+									cudaGraphDestroy(graph);
+								QTB_CUDA(cap != cudaSuccess ? cap : cudaErrorUnknown);
+							}
+							const cudaError_t inst = cudaGraphInstantiate(&panel_exec, graph, 0);
+							cudaGraphDestroy(graph);
+							QTB_CUDA(inst);
 						}
 						QTB_CUDA(cudaGraphLaunch(panel_exec, L.stream));
 						ctx.counters[0] += panel_steps;
