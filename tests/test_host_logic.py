@@ -65,3 +65,45 @@ def test_gemm_warp_grid_exhaustive():
         assert "8 8 -> 2x2 grid, 4x4 atoms" in out.stdout
         assert "1 8 -> 1x4 grid, 1x2 atoms" in out.stdout
         assert "8 1 -> 4x1 grid, 2x1 atoms" in out.stdout
+
+
+def _parallel_last_index(v, tol, pw, min_size, max_size):
+    """the truncation rule as svd_select_kernel (quantit_b200/csrc/qtb_svd.cu) evaluates it: suffix sums S_i of |v|^pow,
+    the largest index i >= min_size with S_i > tol^pow and i < max_size (max_size < 0: no cap); the minimum - 1 when no
+    index qualifies; n - 1 when the reference's loop would not run at all (min_size > n - 1)."""
+    import numpy as np
+
+    n = len(v)
+    if min_size > n - 1:
+        return n - 1
+    s = np.cumsum((np.abs(v) ** pw)[::-1])[::-1]
+    ok = [i for i in range(min_size, n) if s[i] > tol ** pw and (max_size < 0 or i < max_size)]
+    return max(ok) if ok else min_size - 1
+
+
+def test_device_select_rule_equals_reference_loop():
+    """compute_last_index (reference sources/LinearAlgebra.cpp:57-75, restated as a loop in the oracle) against the
+    closed form the device kernel uses, on inputs whose sums are exact in fp64 (powers of two) so that the comparison
+    with tol^pow cannot depend on the summation order: ties, zeros, every min / max combination, tol = 0."""
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import qtb_oracle as orc
+
+    rng = np.random.default_rng(0)
+    checked = 0
+    for _ in range(3000):
+        n = int(rng.integers(1, 24))
+        v = np.sort(2.0 ** -rng.integers(0, 12, n).astype(float))[::-1]
+        if rng.random() < 0.3:
+            v[int(rng.integers(0, n)):] = 0.0  # exact zeros at the tail (rank-deficient groups)
+        tol = 0.0 if rng.random() < 0.2 else 2.0 ** -float(rng.integers(0, 14))
+        min_size = int(rng.integers(0, n + 3))
+        max_size = int(rng.integers(1, n + 3))
+        want = orc.compute_last_index(v, tol, 2.0, min_size, max_size)
+        got = _parallel_last_index(v, tol, 2.0, min_size, max_size)
+        assert got == want, (v.tolist(), tol, min_size, max_size, got, want)
+        checked += 1
+    assert checked == 3000
